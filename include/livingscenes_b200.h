@@ -1,0 +1,204 @@
+/*
+ * livingscenes_b200.h -- C ABI of the B200-native LivingScenes inference hot path.
+ *
+ * The reference (GradientSpaces/LivingScenes) has NO FFI on this path: it is a plain
+ * Python/PyTorch module API.  This header is therefore the boundary
+ * the new build DEFINES; every entry point cites the reference Python interface it replaces
+ * (paths relative to the reference root).  The Python package `livingscenes_b200` binds these
+ * symbols with ctypes and re-exposes the reference's own names (VecDGCNN_att.forward,
+ * Shape_Prior.encode/decoder, sequential_matcher, nn_matcher,
+ * kabsch_transformation_estimation); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (fp32 unless stated) unless the name ends in _host;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises the device, never allocates or frees caller memory; scratch memory is
+ *    provided by the caller (see the *_workspace_bytes functions);
+ *  - return value: 0 = ok, negative = error (LS_ERR_*); ls_last_error() gives the message of
+ *    the last failing call on the calling thread;
+ *  - indices at the boundary are int64 like the reference's (torch.long).
+ */
+#ifndef LIVINGSCENES_B200_H
+#define LIVINGSCENES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LS_API __attribute__((visibility("default")))
+#else
+#define LS_API
+#endif
+
+#define LS_ABI_VERSION 1
+#define LS_MAX_LAYERS 8
+#define LS_KNN_K 16          /* num_knn of the shipped model (model_config.yaml:165) */
+#define LS_HEAD_C 16         /* atten_multi_head_c (model_config.yaml:143)           */
+#define LS_CODE_FLOATS 1028  /* packed embedding record: z_so3 768 | z_inv 256 | s 1 | t 3 */
+
+#define LS_OK 0
+#define LS_ERR_INVALID -1     /* bad argument / unsupported configuration */
+#define LS_ERR_CUDA -2        /* a CUDA runtime call or launch failed     */
+#define LS_ERR_WORKSPACE -3   /* workspace too small                      */
+
+LS_API int ls_version(void);
+LS_API const char* ls_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Encoder: VecDGCNN_att.forward  (lib_shape_prior/core/lib/vec_sim3/vec_dgcnn_atten.py:177-252)
+ * and Shape_Prior.encode         (model_utils.py:165-197) when `normalize` != 0.
+ *
+ * Weights are passed pre-folded (fp64 products rounded to fp32, done once by the host):
+ * with W = lin.weight = [W_a | W_b] (columns acting on nn-dst and on dst, vec_dgcnn_atten.py:160)
+ * and Wd = act.lin_dir.weight (vec_layers.py:246), the per-edge VN-Linear pair
+ *      q = W [nn-dst; dst],   k = Wd q
+ * is evaluated as  q = (W_a src)[idx] + ((W_b-W_a) dst),  k = (Wd W_a src)[idx] + (Wd (W_b-W_a) dst)
+ * i.e. two point-level GEMMs followed by a gather.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ls_enc_layer_desc {
+    int32_t c_in;         /* channels of the incoming features (feat_dim[i-1]; 1 for layer 0)     */
+    int32_t c_out;        /* feat_dim[i]; multiple of 32                                          */
+    int32_t down_factor;  /* FPS down-sampling factor applied before this layer (1 = none)       */
+    int32_t attention;    /* 0: mean pool over K (layers < atten_start_layer), 1: attention pool */
+    int32_t global_conv;  /* 1: followed by the global-context VecLNA (use_res_global_conv)      */
+    int32_t _pad;
+    /* layer 0 (c_in == 1): [2][c_out][3] = { V.lin.weight , V.act.lin_dir.weight @ V.lin.weight } */
+    const float* w0;
+    /* layers >= 1, row blocks of c_out rows each, row-major [rows][c_in]:
+     *   w_src: { Vq=W_a, Vk=(Wd W)_a [, Kq, Kk] }                        (2 or 4 blocks)
+     *   w_dst: { Vq=W_b-W_a, Vk=(Wd W)_b-(Wd W)_a [, Kq, Kk, Qq=W_Q, Qk=Wd_Q W_Q] } (2 or 6 blocks) */
+    const float* w_src;
+    const float* w_dst;
+    /* global conv: [2*c_out][c_out] each: { W_G[:, :c_out]; (Wd_G W_G)[:, :c_out] } and the same
+     * for the [:, c_out:] columns that multiply the instance mean (vec_dgcnn_atten.py:222-225)   */
+    const float* w_g1;
+    const float* w_g2;
+} ls_enc_layer_desc;
+
+typedef struct ls_encoder_desc {
+    int32_t num_layers;
+    int32_t c_dim;              /* 256 */
+    int32_t center_pred;        /* fc_center present */
+    int32_t center_pred_scale;  /* center *= scale_factor */
+    float scale_factor;         /* 64000 */
+    float neg_slope;            /* 0.2 */
+    ls_enc_layer_desc layers[LS_MAX_LAYERS];
+    const float* w_conv_c;   /* [c_dim+1][feat_last]: conv_c.lin.weight then the single shared
+                                direction row conv_c.act.lin_dir.weight @ conv_c.lin.weight       */
+    const float* w_inv_t;    /* [c_dim][c_dim]      fc_inv.weight TRANSPOSED ([in][out])          */
+    const float* w_fc0_t;    /* [c_dim][2*(c_dim/2)] fc_center.fc0: {lin.weight, lin_dir@lin}^T   */
+    const float* w_lin1;     /* [c_dim/2]  fc_center.lin1.weight                                  */
+    const float* w_short;    /* [c_dim]    fc_center.shortcut.weight                              */
+    float w_act2;            /* fc_center.act2.lin_dir.weight (1x1)                               */
+    int32_t _pad;
+} ls_encoder_desc;
+
+typedef struct ls_encoder_io {
+    const float* x;        /* [B,3,N] input cloud (reference layout)                              */
+    int32_t B, N;
+    int32_t normalize;     /* 0: VecDGCNN_att.forward(x);  1: Shape_Prior.encode(x) semantics:
+                              centroid removal, scale_0 = mean(top5(cdist)), t = center+centroid,
+                              s = scale_0*scale (model_utils.py:171-195)                          */
+    int32_t _pad;
+    /* outputs (required) */
+    float* center;         /* [B,3]   (normalize=1: "t")                                          */
+    float* scale;          /* [B]     (normalize=1: "s")                                          */
+    float* z_so3;          /* [B,c_dim,3]                                                         */
+    float* z_inv;          /* [B,c_dim]                                                           */
+    float* packed;         /* optional [B][LS_CODE_FLOATS] record for the embedding all-gather    */
+    /* optional taps (NULL = not wanted) */
+    int64_t* knn_idx[LS_MAX_LAYERS];  /* [B,Nd_l,16] ascending distance, ties -> lower index      */
+    int64_t* fps_idx[LS_MAX_LAYERS];  /* [B,Nd_l] for layers with down_factor > 1                 */
+    float* feat[LS_MAX_LAYERS];       /* [B,c_out_l,3,Nd_l] layer outputs                         */
+    float* scale0;                    /* [B]   (normalize=1)                                      */
+    float* x_norm;                    /* [B,3,N] (normalize=1)                                    */
+    /* optional teacher forcing (NULL = compute): graph given by the caller                     */
+    const int64_t* force_knn_idx[LS_MAX_LAYERS];
+    const int64_t* force_fps_idx[LS_MAX_LAYERS];
+} ls_encoder_io;
+
+LS_API int ls_encoder_workspace_bytes(const ls_encoder_desc* desc, int32_t B, int32_t N, size_t* bytes);
+LS_API int ls_encoder_forward(const ls_encoder_desc* desc, const ls_encoder_io* io,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone graph ops (the pytorch3d boundary of the reference)
+ * ------------------------------------------------------------------------------------------ */
+/* pytorch3d.ops.knn_points as called at vec_dgcnn_atten.py:139: K = 16 nearest of every query
+ * among the sources in D-dim feature space, squared L2 accumulated in fp32 over d = 0..D-1.
+ * query [B,D,Nq], source [B,D,Ns] (channel-major, i.e. the reshape(B, C*3, N) view of :138).
+ * idx [B,Nq,16] int64; dist2 optional [B,Nq,16]. */
+LS_API int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns,
+           int64_t* idx, float* dist2, void* stream);
+
+/* pytorch3d.ops.sample_farthest_points(points, K=n_out), random_start_point=False
+ * (vec_dgcnn_atten.py:169; model_utils.py:205; more_solver.py:67,107-108).
+ * xyz [B,3,N] -> idx [B,n_out] int64, optional out_xyz [B,3,n_out]. */
+LS_API int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz,
+           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Matching: lib_more/matcher_new.py
+ * ------------------------------------------------------------------------------------------ */
+/* sequential_matcher(m0[n,dim], m1[m,dim]) (matcher_new.py:109-139) for `n_pairs` independent
+ * scene pairs: pair p uses rows [off0[p], off0[p+1]) of z0 and [off1[p], off1[p+1]) of z1.
+ * matches0 / matches1 are int64, -1 = unmatched, indices local to the pair.
+ * off0_host / off1_host are HOST arrays of n_pairs+1 ints.  scratch: ls_match_workspace_bytes. */
+LS_API int ls_match_workspace_bytes(const int32_t* off0_host, const int32_t* off1_host, int32_t n_pairs,
+                             size_t* bytes);
+LS_API int ls_seq_match(const float* z0, const float* z1, int32_t dim, const int32_t* off0_host,
+                 const int32_t* off1_host, int32_t n_pairs, int64_t* matches0, int64_t* matches1,
+                 void* workspace, size_t workspace_bytes, void* stream);
+/* nn_matcher (matcher_new.py:85-105): cosine top-1 both ways + mutual check; same batching. */
+LS_API int ls_mutual_nn(const float* z0, const float* z1, int32_t dim, const int32_t* off0_host,
+                 const int32_t* off1_host, int32_t n_pairs, int64_t* matches0, int64_t* matches1,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pose: kabsch_transformation_estimation (lib_more/pose_estimation.py:29-121)
+ * x1, x2 [b,n,3]; weights optional [b,n] (NULL = ones); normalize_w, eps as in the reference.
+ * R [b,3,3], t [b,3] (the reference's [b,3,1]), res [b,n] residual norms.
+ * ------------------------------------------------------------------------------------------ */
+LS_API int ls_kabsch_batched(const float* x1, const float* x2, const float* weights, int32_t b, int32_t n,
+                      int32_t normalize_w, float eps, float* R, float* t, float* res, void* stream);
+/* Pose fit straight from two embedding sets as more_solver.py:114-116 does: x1 = z_so3_a[i] + t_a[i],
+ * x2 = z_so3_b[match[i]] + t_b[match[i]] (pairs with match < 0 get identity / zeros). */
+LS_API int ls_kabsch_from_codes(const float* z_so3_a, const float* t_a, const float* z_so3_b, const float* t_b,
+                         const int64_t* match, int32_t n_pairs, int32_t c_dim, float* R, float* t,
+                         float* res, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SDF query: FieldWrapper.forward (model_utils.py:230-263, inner_deepsdf branch) +
+ * DeepSDF_Decoder.forward (lib_shape_prior/core/lib/implicit_func/deepsdf_decoder.py:78-123)
+ * Weight-norm is pre-folded by the host (W = g * v / |v|_row).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ls_decoder_desc {
+    int32_t latent;        /* 256 */
+    int32_t hidden;        /* 768 */
+    int32_t n_layers;      /* 9   */
+    int32_t latent_in;     /* 4: layer whose input is cat[h, u]                                   */
+    const float* w[12];    /* effective weights, row-major [out][in_padded]; in_padded = in rounded
+                              up to a multiple of 8 (zero filled); layer 0 only holds the columns of
+                              [inner, |q|] (257 -> 264); layer latent_in holds [h(255) | inner,|q| (257)] */
+    const float* b[12];    /* biases [out]                                                       */
+    const float* w0_zinv;  /* [hidden][latent] columns of layer 0 that multiply z_inv             */
+    const float* w4_zinv;  /* [hidden][latent] columns of layer latent_in that multiply z_inv     */
+    int32_t out_dims[12];  /* 768,768,768,255,768,768,768,768,1                                   */
+    int32_t in_dims[12];   /* K of each GEMM (un-padded): 257,768,768,768,512,768,768,768,768     */
+} ls_decoder_desc;
+
+LS_API int ls_sdf_workspace_bytes(const ls_decoder_desc* desc, int32_t B, int32_t M, size_t* bytes);
+/* query [B,M,3] world coordinates; codes z_so3 [B,latent,3], z_inv [B,latent], s [B], t [B,3];
+ * sdf [B,M] (tanh output; occupancy logits of the reference are -sdf). */
+LS_API int ls_sdf_decode(const ls_decoder_desc* desc, const float* query, const float* z_so3,
+                  const float* z_inv, const float* s, const float* t, int32_t B, int32_t M,
+                  float* sdf, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIVINGSCENES_B200_H */

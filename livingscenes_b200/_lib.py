@@ -1,0 +1,132 @@
+"""ctypes binding of the C ABI declared in include/livingscenes_b200.h.
+
+There is NO CPU fallback: if the shared library cannot be loaded every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ls_b200.so")
+
+LS_MAX_LAYERS = 8
+LS_KNN_K = 16
+LS_HEAD_C = 16
+LS_CODE_FLOATS = 1028
+
+c_float_p = C.POINTER(C.c_float)
+c_i64_p = C.POINTER(C.c_int64)
+c_i32_p = C.POINTER(C.c_int32)
+
+
+class EncLayerDesc(C.Structure):
+    _fields_ = [
+        ("c_in", C.c_int32), ("c_out", C.c_int32), ("down_factor", C.c_int32),
+        ("attention", C.c_int32), ("global_conv", C.c_int32), ("_pad", C.c_int32),
+        ("w0", C.c_void_p), ("w_src", C.c_void_p), ("w_dst", C.c_void_p),
+        ("w_g1", C.c_void_p), ("w_g2", C.c_void_p),
+    ]
+
+
+class EncoderDesc(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int32), ("c_dim", C.c_int32), ("center_pred", C.c_int32),
+        ("center_pred_scale", C.c_int32), ("scale_factor", C.c_float), ("neg_slope", C.c_float),
+        ("layers", EncLayerDesc * LS_MAX_LAYERS),
+        ("w_conv_c", C.c_void_p), ("w_inv_t", C.c_void_p), ("w_fc0_t", C.c_void_p),
+        ("w_lin1", C.c_void_p), ("w_short", C.c_void_p), ("w_act2", C.c_float), ("_pad", C.c_int32),
+    ]
+
+
+class EncoderIO(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("B", C.c_int32), ("N", C.c_int32), ("normalize", C.c_int32), ("_pad", C.c_int32),
+        ("center", C.c_void_p), ("scale", C.c_void_p), ("z_so3", C.c_void_p), ("z_inv", C.c_void_p),
+        ("packed", C.c_void_p),
+        ("knn_idx", C.c_void_p * LS_MAX_LAYERS), ("fps_idx", C.c_void_p * LS_MAX_LAYERS),
+        ("feat", C.c_void_p * LS_MAX_LAYERS),
+        ("scale0", C.c_void_p), ("x_norm", C.c_void_p),
+        ("force_knn_idx", C.c_void_p * LS_MAX_LAYERS), ("force_fps_idx", C.c_void_p * LS_MAX_LAYERS),
+    ]
+
+
+class DecoderDesc(C.Structure):
+    _fields_ = [
+        ("latent", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("latent_in", C.c_int32),
+        ("w", C.c_void_p * 12), ("b", C.c_void_p * 12),
+        ("w0_zinv", C.c_void_p), ("w4_zinv", C.c_void_p),
+        ("out_dims", C.c_int32 * 12), ("in_dims", C.c_int32 * 12),
+    ]
+
+
+_PROTOS = {
+    "ls_version": (C.c_int, []),
+    "ls_last_error": (C.c_char_p, []),
+    "ls_encoder_workspace_bytes": (C.c_int, [C.POINTER(EncoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_encoder_forward": (C.c_int, [C.POINTER(EncoderDesc), C.POINTER(EncoderIO), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_fps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_match_workspace_bytes": (C.c_int, [c_i32_p, c_i32_p, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_seq_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, c_i32_p, c_i32_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ls_mutual_nn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, c_i32_p, c_i32_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ls_kabsch_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_kabsch_from_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_sdf_workspace_bytes": (C.c_int, [C.POINTER(DecoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_sdf_decode": (C.c_int, [C.POINTER(DecoderDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # number of C-ABI compute calls issued (bench bookkeeping)
+
+
+def lib():
+    """The loaded shared library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"livingscenes_b200: CUDA extension {LIB_PATH} is missing. Build it with "
+                        "`python -m livingscenes_b200._build` (needs nvcc); there is no CPU fallback.")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in _PROTOS.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ls_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def ptr(t):
+    """Device pointer of a tensor as an int (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"livingscenes_b200: `{name}` must be a CUDA tensor; this package has no CPU path "
+            "(the CPU restatement lives in oracle/ and is test infrastructure only).")

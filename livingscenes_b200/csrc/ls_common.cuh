@@ -1,0 +1,100 @@
+// Shared device helpers and host-side error plumbing for the livingscenes_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/livingscenes_b200.h"
+
+namespace ls {
+
+void set_error(const std::string& msg);
+
+#define LS_CHECK_CUDA(expr)                                                                 \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ls::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+            return LS_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+#define LS_CHECK_LAUNCH(name)                                                               \
+    do {                                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess) {                                                            \
+            ls::set_error(std::string("launch of ") + name + ": " + cudaGetErrorString(_e)); \
+            return LS_ERR_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+#define LS_REQUIRE(cond, msg)                                                               \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            ls::set_error(std::string("invalid argument: ") + msg);                         \
+            return LS_ERR_INVALID;                                                          \
+        }                                                                                   \
+    } while (0)
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float EPS_NRM = 1e-12f;   // F.normalize eps
+constexpr float EPS_NRM2 = 1e-24f;  // its square, for the sqrt-free VN activation
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+// reductions inside each aligned group of 16 lanes
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float half_max(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// VN leaky-ReLU on one 3-vector (vec_layers.py:241-268, so3 mode) in sqrt-free form:
+//   out = q + (lrelu(p) - p) * khat,  p = <q, khat>,  khat = k / max(|k|, 1e-12)
+//       = q - (1 - slope) * min(<q,k>, 0) / max(|k|^2, 1e-24) * k
+__device__ __forceinline__ void vn_act(float q0, float q1, float q2, float k0, float k1, float k2,
+                                       float one_minus_slope, float& o0, float& o1, float& o2) {
+    float n2 = fmaf(k2, k2, fmaf(k1, k1, k0 * k0));
+    float dt = fmaf(q2, k2, fmaf(q1, k1, q0 * k0));
+    float t = one_minus_slope * fminf(dt, 0.f) / fmaxf(n2, EPS_NRM2);
+    o0 = fmaf(-t, k0, q0);
+    o1 = fmaf(-t, k1, q1);
+    o2 = fmaf(-t, k2, q2);
+}
+
+// ---- GEMM launcher shared by the encoder and the SDF decoder (ls_gemm.cu) -------------------
+struct GemmArgs {
+    const float* W;   // [R][ldw] row-major, ldw >= K, ldw % 4 == 0, zero padded beyond K
+    const float* X;   // element (b, k, n) at X[b*x_sb + k*x_sk + n]
+    float* out;
+    int R, K, ldw;
+    int n_per_b;      // columns per instance (n3)
+    int B;
+    long long x_sb, x_sk;
+    // store mode 0 (channel major): out[b*o_sb + r*o_sr + n]
+    long long o_sb, o_sr;
+    // store mode 1 (point major gather table): out[((b*npts + pt) * R*3) + (part*3+axis)*c_out + c]
+    int point_major, npts, c_out;
+    // epilogue: + bias[b*bias_sb + r*bias_sr + axis*(bias_axis)] with axis = n / npts; relu
+    const float* bias;
+    long long bias_sb, bias_sr;
+    int bias_axis;
+    int relu;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t st);
+
+}  // namespace ls

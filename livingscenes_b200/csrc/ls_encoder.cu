@@ -1,0 +1,414 @@
+// Host orchestration of the encoder path behind the C ABI (include/livingscenes_b200.h):
+//   ls_encoder_forward   VecDGCNN_att.forward / Shape_Prior.encode
+//   ls_knn, ls_fps       the pytorch3d boundary as stand-alone ops
+#include <algorithm>
+#include <vector>
+
+#include "ls_encoder_kernels.cuh"
+
+namespace ls {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+struct Plan {
+    int n_src[LS_MAX_LAYERS], n_dst[LS_MAX_LAYERS];
+    float *xn, *centroid, *s0, *featA, *featB, *dstf, *pooled, *raw, *psrc, *pdst, *bias;
+    int* sel[LS_MAX_LAYERS];
+    size_t bytes;
+};
+
+int check_desc(const ls_encoder_desc* d, int N) {
+    LS_REQUIRE(d != nullptr, "null encoder descriptor");
+    LS_REQUIRE(d->num_layers >= 1 && d->num_layers <= LS_MAX_LAYERS, "num_layers out of range");
+    LS_REQUIRE(d->c_dim % 32 == 0 && d->c_dim >= 32 && d->c_dim <= 1024, "c_dim must be a multiple of 32 <= 1024");
+    int n = N;
+    for (int i = 0; i < d->num_layers; ++i) {
+        const ls_enc_layer_desc& L = d->layers[i];
+        LS_REQUIRE(L.c_out % 32 == 0 && L.c_out >= 32 && L.c_out <= 512, "c_out must be a multiple of 32 in [32,512]");
+        LS_REQUIRE(L.down_factor >= 1, "down_factor must be >= 1");
+        if (i == 0) {
+            LS_REQUIRE(L.c_in == 1 && !L.attention && !L.global_conv && L.down_factor == 1 && L.w0,
+                       "layer 0 must be the plain xyz EdgeConv layer");
+        } else {
+            LS_REQUIRE(L.c_in == d->layers[i - 1].c_out, "c_in must equal the previous layer's c_out");
+            LS_REQUIRE(L.c_in % 8 == 0, "c_in must be a multiple of 8");
+            LS_REQUIRE(L.w_src && L.w_dst, "missing folded weights");
+            LS_REQUIRE(!L.global_conv || (L.w_g1 && L.w_g2), "missing global-conv weights");
+            int cpl = L.c_out / 32;
+            LS_REQUIRE(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8 || cpl == 16, "c_out/32 must be a power of two <= 16");
+        }
+        LS_REQUIRE(n % L.down_factor == 0, "N must be divisible by the down-sampling factors");
+        n /= L.down_factor;
+        LS_REQUIRE(n >= LS_KNN_K, "too few points for K=16 neighbours at a deep layer (N too small)");
+    }
+    LS_REQUIRE(d->w_conv_c && d->w_inv_t, "missing head weights");
+    LS_REQUIRE(!d->center_pred || (d->w_fc0_t && d->w_lin1 && d->w_short), "missing fc_center weights");
+    return LS_OK;
+}
+
+void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
+    Carver c(ws);
+    size_t feat = 0, dstf = 0, pooled = 0, raw = 0, psrc = 0, pdst = 0, bias = 0;
+    int n = N;
+    for (int i = 0; i < d->num_layers; ++i) {
+        const ls_enc_layer_desc& L = d->layers[i];
+        p.n_src[i] = n;
+        n /= L.down_factor;
+        p.n_dst[i] = n;
+        const size_t co = L.c_out, ci = L.c_in;
+        feat = std::max(feat, co * 3 * (size_t)n);
+        if (L.down_factor > 1) dstf = std::max(dstf, ci * 3 * (size_t)n);
+        if (L.global_conv) {
+            pooled = std::max(pooled, co * 3 * (size_t)n);
+            raw = std::max(raw, 2 * co * 3 * (size_t)n);
+            bias = std::max(bias, 2 * co * 3);
+        }
+        if (i > 0) {
+            const size_t nb = L.attention ? 2 : 1;
+            psrc = std::max(psrc, 2 * nb * co * 3 * (size_t)p.n_src[i]);
+            pdst = std::max(pdst, (2 * nb + (L.attention ? 2 : 0)) * co * 3 * (size_t)n);
+        }
+    }
+    raw = std::max(raw, (size_t)(d->c_dim + 1) * 3 * n);
+    p.xn = c.take<float>((size_t)B * 3 * N);
+    p.centroid = c.take<float>((size_t)B * 3);
+    p.s0 = c.take<float>((size_t)B);
+    p.featA = c.take<float>((size_t)B * feat);
+    p.featB = c.take<float>((size_t)B * feat);
+    p.dstf = c.take<float>((size_t)B * std::max<size_t>(dstf, 1));
+    p.pooled = c.take<float>((size_t)B * std::max<size_t>(pooled, 1));
+    p.raw = c.take<float>((size_t)B * raw);
+    p.psrc = c.take<float>((size_t)B * std::max<size_t>(psrc, 1));
+    p.pdst = c.take<float>((size_t)B * std::max<size_t>(pdst, 1));
+    p.bias = c.take<float>((size_t)B * std::max<size_t>(bias, 1));
+    for (int i = 0; i < d->num_layers; ++i)
+        p.sel[i] = d->layers[i].down_factor > 1 ? c.take<int>((size_t)B * p.n_dst[i]) : nullptr;
+    p.bytes = (c.off + 255) & ~size_t(255);
+}
+
+template <int MODE>
+int launch_edge_cpl(const EdgeArgs& a, int cpl, dim3 grid, cudaStream_t st) {
+    switch (cpl) {
+        case 1: k_knn_edge<MODE, 1><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+        case 2: k_knn_edge<MODE, 2><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+        case 4: k_knn_edge<MODE, 4><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+        case 8: k_knn_edge<MODE, 8><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+        case 16: k_knn_edge<MODE, 16><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+        default: set_error("unsupported c_out/32"); return LS_ERR_INVALID;
+    }
+    LS_CHECK_LAUNCH("k_knn_edge");
+    return LS_OK;
+}
+
+int launch_edge(int mode, const EdgeArgs& a, cudaStream_t st) {
+    dim3 grid((a.Nd + QT - 1) / QT, a.B);
+    const int cpl = a.Co / 32;
+    if (mode == MODE_L0) return launch_edge_cpl<MODE_L0>(a, cpl, grid, st);
+    if (mode == MODE_MEAN) return launch_edge_cpl<MODE_MEAN>(a, cpl, grid, st);
+    if (mode == MODE_ATT) return launch_edge_cpl<MODE_ATT>(a, cpl, grid, st);
+    k_knn_edge<MODE_KNN_ONLY, 1><<<grid, EDGE_THREADS, 0, st>>>(a);
+    LS_CHECK_LAUNCH("k_knn_only");
+    return LS_OK;
+}
+
+int launch_fps(const FpsArgs& a, int B, cudaStream_t st) {
+    const int N = a.N;
+    LS_REQUIRE(N >= 1 && N <= 8192, "fps: N must be in [1, 8192] (in-register running min distance)");
+    for (int l = 0; l < a.n_levels; ++l) {
+        int prev = l == 0 ? N : a.n_out[l - 1];
+        LS_REQUIRE(a.n_out[l] >= 1 && a.n_out[l] <= prev, "fps: n_out must not exceed the number of points");
+    }
+    int T = 128;
+    while (T < 1024 && T * 2 <= N) T *= 2;  // ~1-2 points per thread for N <= 2048
+    const int ppt = (N + T - 1) / T;
+    const size_t smem = (size_t)(3 * N + 4 * a.n_out[0]) * sizeof(float);
+#define LS_FPS_CASE(P)                                                                              \
+    {                                                                                               \
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_fps<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_fps<P><<<B, T, smem, st>>>(a);                                                            \
+    }
+    if (ppt <= 1) LS_FPS_CASE(1)
+    else if (ppt <= 2) LS_FPS_CASE(2)
+    else if (ppt <= 4) LS_FPS_CASE(4)
+    else LS_FPS_CASE(8)
+#undef LS_FPS_CASE
+    LS_CHECK_LAUNCH("k_fps");
+    return LS_OK;
+}
+
+}  // namespace
+}  // namespace ls
+
+using namespace ls;
+
+extern "C" {
+
+int ls_version(void) { return LS_ABI_VERSION; }
+const char* ls_last_error(void) { return ls::g_last_error.c_str(); }
+
+int ls_encoder_workspace_bytes(const ls_encoder_desc* desc, int32_t B, int32_t N, size_t* bytes) {
+    LS_REQUIRE(bytes != nullptr && B >= 1 && N >= 1, "bad arguments");
+    int rc = check_desc(desc, N);
+    if (rc != LS_OK) return rc;
+    Plan p;
+    make_plan(desc, B, N, nullptr, p);
+    *bytes = p.bytes;
+    return LS_OK;
+}
+
+int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    LS_REQUIRE(io != nullptr && io->x != nullptr, "null io");
+    const int B = io->B, N = io->N;
+    LS_REQUIRE(B >= 1 && N >= 1 && B <= 65535, "B must be in [1, 65535]");
+    int rc = check_desc(d, N);
+    if (rc != LS_OK) return rc;
+    LS_REQUIRE(io->scale && io->z_so3 && io->z_inv, "missing output pointers");
+    LS_REQUIRE(!d->center_pred || io->center, "center output required when center_pred is set");
+    LS_REQUIRE(workspace != nullptr, "null workspace");
+    Plan p;
+    make_plan(d, B, N, workspace, p);
+    if (p.bytes > workspace_bytes) {
+        set_error("workspace too small");
+        return LS_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float oms = 1.f - d->neg_slope;
+
+    // ---- pre-processing (Shape_Prior.encode) ------------------------------------------------
+    const float* x = io->x;
+    if (io->normalize) {
+        const size_t smem = (size_t)(3 * N + 64) * sizeof(float);
+        LS_REQUIRE(smem <= 200 * 1024, "normalize: N too large for the shared-memory resident cloud");
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_normalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_normalize<<<B, NORM_THREADS, smem, st>>>(io->x, N, p.xn, p.centroid, p.s0);
+        LS_CHECK_LAUNCH("k_normalize");
+        x = p.xn;
+        if (io->scale0) LS_CHECK_CUDA(cudaMemcpyAsync(io->scale0, p.s0, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+        if (io->x_norm)
+            LS_CHECK_CUDA(cudaMemcpyAsync(io->x_norm, p.xn, sizeof(float) * (size_t)B * 3 * N, cudaMemcpyDeviceToDevice, st));
+    }
+
+    // ---- FPS chain: all down-sampling selections depend on xyz only --------------------------
+    {
+        FpsArgs fa{};
+        fa.xyz = x;
+        fa.N = N;
+        fa.n_levels = 0;
+        for (int i = 0; i < d->num_layers; ++i) {
+            if (d->layers[i].down_factor > 1) {
+                LS_REQUIRE(fa.n_levels < FPS_MAX_LEVELS, "too many down-sampling layers");
+                fa.n_out[fa.n_levels] = p.n_dst[i];
+                fa.sel32[fa.n_levels] = p.sel[i];
+                fa.sel64[fa.n_levels] = io->fps_idx[i];
+                fa.force[fa.n_levels] = io->force_fps_idx[i];
+                ++fa.n_levels;
+            }
+        }
+        if (fa.n_levels > 0) {
+            rc = launch_fps(fa, B, st);
+            if (rc != LS_OK) return rc;
+        }
+    }
+
+    // ---- layers -------------------------------------------------------------------------------
+    const float* src_f = x;  // [B][C*3][Ns]
+    float* bufs[2] = {p.featA, p.featB};
+    int cur = 0;
+    for (int i = 0; i < d->num_layers; ++i) {
+        const ls_enc_layer_desc& L = d->layers[i];
+        const int Ns = p.n_src[i], Nd = p.n_dst[i], Ci = L.c_in, Co = L.c_out;
+        const float* dst_f = src_f;
+        if (L.down_factor > 1) {
+            dim3 g((Nd + 127) / 128, Ci * 3, B);
+            k_gather_points<<<g, 128, 0, st>>>(src_f, p.sel[i], Ci * 3, Ns, Nd, p.dstf);
+            LS_CHECK_LAUNCH("k_gather_points");
+            dst_f = p.dstf;
+        }
+        float* layer_out = bufs[cur];
+        float* edge_out = L.global_conv ? p.pooled : layer_out;
+
+        EdgeArgs ea{};
+        ea.src_f = src_f;
+        ea.dst_f = dst_f;
+        ea.B = B;
+        ea.D = Ci * 3;
+        ea.Ns = Ns;
+        ea.Nd = Nd;
+        ea.Co = Co;
+        ea.oms = oms;
+        ea.out = edge_out;
+        ea.idx_out = io->knn_idx[i];
+        ea.idx_in = io->force_knn_idx[i];
+        if (i == 0) {
+            ea.w0 = L.w0;
+            rc = launch_edge(MODE_L0, ea, st);
+            if (rc != LS_OK) return rc;
+        } else {
+            const int nb = L.attention ? 2 : 1;
+            const int r_src = 2 * nb * Co, r_dst = (2 * nb + (L.attention ? 2 : 0)) * Co;
+            GemmArgs g{};
+            g.K = Ci;
+            g.ldw = Ci;
+            g.B = B;
+            g.point_major = 1;
+            g.c_out = Co;
+            // source table
+            g.W = L.w_src;
+            g.R = r_src;
+            g.X = src_f;
+            g.n_per_b = 3 * Ns;
+            g.npts = Ns;
+            g.x_sb = (long long)Ci * 3 * Ns;
+            g.x_sk = 3LL * Ns;
+            g.out = p.psrc;
+            rc = launch_gemm(g, st);
+            if (rc != LS_OK) return rc;
+            // dst table
+            g.W = L.w_dst;
+            g.R = r_dst;
+            g.X = dst_f;
+            g.n_per_b = 3 * Nd;
+            g.npts = Nd;
+            g.x_sb = (long long)Ci * 3 * Nd;
+            g.x_sk = 3LL * Nd;
+            g.out = p.pdst;
+            rc = launch_gemm(g, st);
+            if (rc != LS_OK) return rc;
+            ea.psrc = p.psrc;
+            ea.pdst = p.pdst;
+            ea.row_s = r_src * 3;
+            ea.row_d = r_dst * 3;
+            rc = launch_edge(L.attention ? MODE_ATT : MODE_MEAN, ea, st);
+            if (rc != LS_OK) return rc;
+        }
+        if (L.global_conv) {
+            k_mean_bias<<<B, 256, (size_t)Co * 3 * sizeof(float), st>>>(p.pooled, Co, Nd, L.w_g2, p.bias);
+            LS_CHECK_LAUNCH("k_mean_bias");
+            GemmArgs g{};
+            g.W = L.w_g1;
+            g.R = 2 * Co;
+            g.K = Co;
+            g.ldw = Co;
+            g.B = B;
+            g.X = p.pooled;
+            g.n_per_b = 3 * Nd;
+            g.npts = Nd;
+            g.x_sb = (long long)Co * 3 * Nd;
+            g.x_sk = 3LL * Nd;
+            g.out = p.raw;
+            g.o_sb = 2LL * Co * 3 * Nd;
+            g.o_sr = 3LL * Nd;
+            g.bias = p.bias;
+            g.bias_sb = 2LL * Co * 3;
+            g.bias_sr = 3;
+            g.bias_axis = 1;
+            rc = launch_gemm(g, st);
+            if (rc != LS_OK) return rc;
+            dim3 gv((Nd + 127) / 128, Co, B);
+            k_vnact<<<gv, 128, 0, st>>>(p.raw, Co, Nd, oms, layer_out);
+            LS_CHECK_LAUNCH("k_vnact");
+        }
+        if (io->feat[i])
+            LS_CHECK_CUDA(cudaMemcpyAsync(io->feat[i], layer_out, sizeof(float) * (size_t)B * Co * 3 * Nd,
+                                          cudaMemcpyDeviceToDevice, st));
+        src_f = layer_out;
+        cur ^= 1;
+    }
+
+    // ---- head ------------------------------------------------------------------------------
+    {
+        const int last = d->num_layers - 1;
+        const int Cl = d->layers[last].c_out, Nl = p.n_dst[last], C = d->c_dim;
+        GemmArgs g{};
+        g.W = d->w_conv_c;
+        g.R = C + 1;
+        g.K = Cl;
+        g.ldw = Cl;
+        g.B = B;
+        g.X = src_f;
+        g.n_per_b = 3 * Nl;
+        g.npts = Nl;
+        g.x_sb = (long long)Cl * 3 * Nl;
+        g.x_sk = 3LL * Nl;
+        g.out = p.raw;
+        g.o_sb = (long long)(C + 1) * 3 * Nl;
+        g.o_sr = 3LL * Nl;
+        rc = launch_gemm(g, st);
+        if (rc != LS_OK) return rc;
+        HeadArgs h{};
+        h.raw = p.raw;
+        h.c_dim = C;
+        h.Nl = Nl;
+        h.w_inv_t = d->w_inv_t;
+        h.w_fc0_t = d->w_fc0_t;
+        h.w_lin1 = d->w_lin1;
+        h.w_short = d->w_short;
+        h.w_act2 = d->w_act2;
+        h.oms = oms;
+        h.scale_factor = d->scale_factor;
+        h.center_pred = d->center_pred;
+        h.center_pred_scale = d->center_pred_scale;
+        h.normalize = io->normalize;
+        h.centroid = p.centroid;
+        h.s0 = p.s0;
+        h.center = io->center;
+        h.scale = io->scale;
+        h.z_so3 = io->z_so3;
+        h.z_inv = io->z_inv;
+        h.packed = io->packed;
+        LS_REQUIRE(!io->packed || C == 256, "packed records assume c_dim == 256");
+        k_head<<<B, C, (size_t)6 * C * sizeof(float), st>>>(h);
+        LS_CHECK_LAUNCH("k_head");
+    }
+    return LS_OK;
+}
+
+int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns,
+           int64_t* idx, float* dist2, void* stream) {
+    LS_REQUIRE(query && source && idx, "null pointer");
+    LS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && Nq >= 1 && Ns >= LS_KNN_K, "bad sizes (need Ns >= 16)");
+    EdgeArgs ea{};
+    ea.src_f = source;
+    ea.dst_f = query;
+    ea.B = B;
+    ea.D = D;
+    ea.Ns = Ns;
+    ea.Nd = Nq;
+    ea.Co = 32;
+    ea.idx_out = idx;
+    ea.dist_out = dist2;
+    return launch_edge(MODE_KNN_ONLY, ea, static_cast<cudaStream_t>(stream));
+}
+
+int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz,
+           void* stream) {
+    LS_REQUIRE(xyz && idx, "null pointer");
+    LS_REQUIRE(B >= 1, "bad batch");
+    FpsArgs fa{};
+    fa.xyz = xyz;
+    fa.N = N;
+    fa.n_levels = 1;
+    fa.n_out[0] = n_out;
+    fa.sel64[0] = idx;
+    fa.out_xyz = out_xyz;
+    return launch_fps(fa, B, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,843 @@
+// Device kernels of the VN-DGCNN+attention encoder (sm_100a).  Host orchestration: ls_encoder.cu.
+// Reference arithmetic: SURVEY.md Appendix A; file:line citations are relative to the reference root.
+#pragma once
+#include <float.h>
+
+#include "ls_common.cuh"
+
+namespace ls {
+
+// ============================================================================================
+// Shape_Prior.encode pre-processing (model_utils.py:171-177): centroid removal and
+// scale_0 = mean of the 5 largest entries of the flattened N x N distance matrix.
+// One CTA per instance; the centred cloud lives in shared memory; every ordered pair (i,j) is
+// visited, so each unordered pair is counted twice exactly like the reference's flattened
+// symmetric matrix (=> scale_0 = (2 d1 + 2 d2 + d3) / 5 for distinct pair distances).
+// ============================================================================================
+constexpr int NORM_THREADS = 512;
+
+__global__ void __launch_bounds__(NORM_THREADS) k_normalize(const float* __restrict__ x, int N,
+                                                            float* __restrict__ xn,
+                                                            float* __restrict__ centroid,
+                                                            float* __restrict__ s0_out) {
+    extern __shared__ float sm[];
+    float* sx = sm;           // [3][N]
+    float* red = sm + 3 * N;  // [NORM_THREADS/32 * 3] + merge scratch
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nw = NORM_THREADS / 32;
+    const float* xb = x + (size_t)b * 3 * N;
+
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int i = t; i < N; i += NORM_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = xb[a * N + i];
+            sx[a * N + i] = v;
+            s[a] += v;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        s[a] = warp_sum(s[a]);
+        if (lane == 0) red[w * 3 + a] = s[a];
+    }
+    __syncthreads();
+    float mu[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float v = 0.f;
+        for (int i = 0; i < nw; ++i) v += red[i * 3 + a];
+        mu[a] = v / (float)N;
+    }
+    __syncthreads();
+    for (int i = t; i < N; i += NORM_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) sx[a * N + i] -= mu[a];
+    }
+    __syncthreads();
+
+    // per-thread top-5 of squared distances over the rows i = t, t+T, ...
+    float top[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+    for (int i = t; i < N; i += NORM_THREADS) {
+        const float xi = sx[i], yi = sx[N + i], zi = sx[2 * N + i];
+        for (int j = 0; j < N; ++j) {
+            float dx = xi - sx[j], dy = yi - sx[N + j], dz = zi - sx[2 * N + j];
+            float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (d2 > top[4]) {
+                top[4] = d2;
+#pragma unroll
+                for (int k = 4; k > 0; --k) {
+                    if (top[k] > top[k - 1]) {
+                        float tmp = top[k];
+                        top[k] = top[k - 1];
+                        top[k - 1] = tmp;
+                    }
+                }
+            }
+        }
+    }
+    // merge: 5 rounds of block-wide max with removal
+    __shared__ float s_best[NORM_THREADS / 32];
+    __shared__ int s_who[NORM_THREADS / 32];
+    __shared__ float s_sel[5];
+    int p = 0;
+    for (int r = 0; r < 5; ++r) {
+        float cand = -1.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            if (k == p) cand = top[k];
+        float v = cand;
+        int who = t;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float v2 = __shfl_xor_sync(FULL, v, o);
+            int w2 = __shfl_xor_sync(FULL, who, o);
+            if (v2 > v || (v2 == v && w2 < who)) {
+                v = v2;
+                who = w2;
+            }
+        }
+        if (lane == 0) {
+            s_best[w] = v;
+            s_who[w] = who;
+        }
+        __syncthreads();
+        float bv = s_best[0];
+        int bw = s_who[0];
+        for (int i = 1; i < nw; ++i) {
+            if (s_best[i] > bv || (s_best[i] == bv && s_who[i] < bw)) {
+                bv = s_best[i];
+                bw = s_who[i];
+            }
+        }
+        if (t == bw) ++p;
+        if (t == 0) s_sel[r] = bv;
+        __syncthreads();
+    }
+    float s0 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) s0 += sqrtf(fmaxf(s_sel[r], 0.f));
+    s0 = s0 / 5.f;
+    if (t == 0) {
+        s0_out[b] = s0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) centroid[b * 3 + a] = mu[a];
+    }
+    float* xo = xn + (size_t)b * 3 * N;
+    for (int i = t; i < N; i += NORM_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xo[a * N + i] = sx[a * N + i] / s0;
+    }
+}
+
+// ============================================================================================
+// Farthest point sampling chain (pytorch3d sample_farthest_points as used at
+// vec_dgcnn_atten.py:163-175): start index 0, min_d update, arg-max with lowest index on ties;
+// d = dx*dx + dy*dy + dz*dz with every operation rounded separately (no FMA contraction) so the
+// selection is bit-identical to the oracle.  FPS only depends on xyz, so the three down-sampling
+// steps of the shipped encoder (N -> N/2 -> N/8 -> N/32) run back to back in ONE launch, one CTA
+// per instance, coordinates in shared memory, running min-distance in registers, one
+// __syncthreads per selected point.
+// ============================================================================================
+constexpr int FPS_MAX_LEVELS = 4;
+struct FpsArgs {
+    const float* xyz;  // [B][3][N]
+    int N;
+    int n_levels;
+    int n_out[FPS_MAX_LEVELS];
+    int* sel32[FPS_MAX_LEVELS];          // optional [B][n_out] int32 (internal use)
+    int64_t* sel64[FPS_MAX_LEVELS];    // optional [B][n_out] int64 (API tap)
+    const int64_t* force[FPS_MAX_LEVELS];  // optional forced selections (teacher forcing)
+    float* out_xyz;                      // optional [B][3][n_out[last]]
+};
+
+template <int PPT>
+__global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
+    extern __shared__ float sm[];
+    const int T = blockDim.x;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
+    const int N = a.N;
+    float* cur = sm;                              // [3][N]
+    float* nxt = sm + 3 * N;                      // [3][n_out[0]]  (ping-pong partner)
+    int* ssel = (int*)(sm + 3 * N + 3 * a.n_out[0]);  // [n_out[0]]
+    __shared__ float wb_v[2][32];
+    __shared__ int wb_i[2][32];
+
+    const float* xb = a.xyz + (size_t)b * 3 * N;
+    for (int i = t; i < 3 * N; i += T) cur[i] = xb[i];
+    __syncthreads();
+
+    int n_cur = N;
+    for (int lv = 0; lv < a.n_levels; ++lv) {
+        const int n_out = a.n_out[lv];
+        if (a.force[lv]) {
+            for (int j = t; j < n_out; j += T) ssel[j] = (int)a.force[lv][(size_t)b * n_out + j];
+            __syncthreads();
+        } else {
+            float px[PPT], py[PPT], pz[PPT], md[PPT];
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) {
+                int i = t + p * T;
+                bool ok = i < n_cur;
+                px[p] = ok ? cur[i] : 0.f;
+                py[p] = ok ? cur[n_cur + i] : 0.f;
+                pz[p] = ok ? cur[2 * n_cur + i] : 0.f;
+                md[p] = ok ? FLT_MAX : -1.f;  // padding can never win the arg-max
+            }
+            int last = 0;
+            if (t == 0) ssel[0] = 0;
+            for (int j = 1; j < n_out; ++j) {
+                const float lx = cur[last], ly = cur[n_cur + last], lz = cur[2 * n_cur + last];
+                float bv = -2.f;
+                int bi = 0x7fffffff;
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    float dx = px[p] - lx, dy = py[p] - ly, dz = pz[p] - lz;
+                    float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    float m = fminf(md[p], d);
+                    if (md[p] >= 0.f) md[p] = m;
+                    if (md[p] > bv) {  // strict: lowest index within the thread wins
+                        bv = md[p];
+                        bi = t + p * T;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float v2 = __shfl_xor_sync(FULL, bv, o);
+                    int i2 = __shfl_xor_sync(FULL, bi, o);
+                    if (v2 > bv || (v2 == bv && i2 < bi)) {
+                        bv = v2;
+                        bi = i2;
+                    }
+                }
+                const int par = j & 1;
+                if (lane == 0) {
+                    wb_v[par][w] = bv;
+                    wb_i[par][w] = bi;
+                }
+                __syncthreads();
+                bv = lane < nw ? wb_v[par][lane] : -2.f;
+                bi = lane < nw ? wb_i[par][lane] : 0x7fffffff;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    float v2 = __shfl_xor_sync(FULL, bv, o);
+                    int i2 = __shfl_xor_sync(FULL, bi, o);
+                    if (v2 > bv || (v2 == bv && i2 < bi)) {
+                        bv = v2;
+                        bi = i2;
+                    }
+                }
+                last = bi;
+                if (t == 0) ssel[j] = last;
+            }
+            __syncthreads();
+        }
+        // publish the selection and build the next level's coordinates (selection order)
+        for (int j = t; j < n_out; j += T) {
+            int s = ssel[j];
+            if (a.sel32[lv]) a.sel32[lv][(size_t)b * n_out + j] = s;
+            if (a.sel64[lv]) a.sel64[lv][(size_t)b * n_out + j] = s;
+            nxt[j] = cur[s];
+            nxt[n_out + j] = cur[n_cur + s];
+            nxt[2 * n_out + j] = cur[2 * n_cur + s];
+        }
+        __syncthreads();
+        float* tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+        n_cur = n_out;
+    }
+    if (a.out_xyz) {
+        float* o = a.out_xyz + (size_t)b * 3 * n_cur;
+        for (int i = t; i < 3 * n_cur; i += T) o[i] = cur[i];
+    }
+}
+
+// dst_f[b][r][j] = src_f[b][r][sel[b][j]]   (vec_dgcnn_atten.py:173; r runs over C*3 rows)
+__global__ void k_gather_points(const float* __restrict__ in, const int* __restrict__ sel, int rows,
+                                int n_in, int n_out, float* __restrict__ out) {
+    const int b = blockIdx.z, r = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_out) return;
+    int s = sel[(size_t)b * n_out + j];
+    out[((size_t)b * rows + r) * n_out + j] = in[((size_t)b * rows + r) * n_in + s];
+}
+
+// ============================================================================================
+// Fused kNN graph + VN-EdgeConv + pooling   (get_graph_feature + V/K/Q VecLNA + mean / attention
+// pool: vec_dgcnn_atten.py:124-161, 197-219; vec_layers.py:121-134, 241-268, 24-31).
+//
+// One CTA = 64 dst points of one instance, 256 threads.
+//   phase 1  brute-force feature-space kNN: 8x8 register tiles of squared distances accumulated in
+//            fp32 in the direct form sum_d (q_d - s_d)^2 over shared-memory staged [d][point] tiles
+//            (64 queries x 256 sources x 8 dims per stage, double buffered); a warp owns 8 queries
+//            and keeps each query's sorted top-16 distributed over lanes 0..15; candidates that
+//            beat the current 16th are merged with ballot/shuffle insertion.  Ties -> lower index.
+//   phase 2  per dst point (one warp, lanes = output channels): gather the 16 neighbours' rows of
+//            the point-level GEMM tables, add the dst term, VN leaky-ReLU, then
+//              MODE_MEAN : mean over the 16 edges                               (layers 0-1)
+//              MODE_ATT  : cevn(K) . cevn(Q) logits per 16-channel head, softmax over the 16
+//                          edges (half-warp shuffles), weighted sum of V        (layers >= 2)
+//              MODE_L0   : layer 0 builds its 3-channel edge feature [cross, nn-dst, dst]
+//                          directly from xyz (vec_dgcnn_atten.py:153-158).
+// ============================================================================================
+constexpr int QT = 64, ST = 256, DKC = 8, EDGE_THREADS = 256;
+enum { MODE_L0 = 0, MODE_MEAN = 1, MODE_ATT = 2, MODE_KNN_ONLY = 3 };
+
+struct EdgeArgs {
+    const float* src_f;  // [B][D][Ns] kNN features of the sources (xyz for layer 0)
+    const float* dst_f;  // [B][D][Nd] kNN features of the queries
+    int B, D, Ns, Nd;
+    const float* psrc;   // [B][Ns][row_s]  gather table  (parts Vq,Vk[,Kq,Kk] x 3 axes x Co)
+    const float* pdst;   // [B][Nd][row_d]  dst table     (parts Vq,Vk[,Kq,Kk,Qq,Qk])
+    int row_s, row_d;
+    const float* w0;     // layer 0: [2][Co][3]
+    int Co;
+    float oms;           // 1 - negative slope
+    float* out;          // [B][Co][3][Nd]
+    int64_t* idx_out;         // optional [B][Nd][16]
+    const int64_t* idx_in;   // optional forced graph
+    float* dist_out;           // optional [B][Nd][16] (MODE_KNN_ONLY)
+};
+
+__device__ __forceinline__ void topk_insert(float& ld, int& li, float cd, int ci, int lane) {
+    const bool worse = (ld > cd) || (ld == cd && li > ci);
+    const unsigned m = __ballot_sync(FULL, worse);
+    const float dn = __shfl_up_sync(FULL, ld, 1);
+    const int in = __shfl_up_sync(FULL, li, 1);
+    const int pos = __ffs(m) - 1;
+    if (lane == pos) {
+        ld = cd;
+        li = ci;
+    } else if (lane > pos) {
+        ld = dn;
+        li = in;
+    }
+}
+
+template <int MODE, int CPL>
+__global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) {
+    // phase-1 tiles and phase-2 scratch share one buffer
+    constexpr int TILE_FLOATS = 2 * DKC * (QT + ST);
+    constexpr int SR_FLOATS = (MODE == MODE_ATT) ? 8 * CPL * 32 : 0;
+    constexpr int BUF_FLOATS = TILE_FLOATS > SR_FLOATS ? TILE_FLOATS : SR_FLOATS;
+    __shared__ __align__(16) float sbuf[BUF_FLOATS];
+    __shared__ int sIdx[QT][LS_KNN_K];
+    __shared__ float sDist[(MODE == MODE_KNN_ONLY) ? QT : 1][LS_KNN_K];
+
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * QT;
+    const int Ns = a.Ns, Nd = a.Nd, D = a.D;
+
+    if (a.idx_in != nullptr) {
+        for (int e = t; e < QT * LS_KNN_K; e += EDGE_THREADS) {
+            int ql = e >> 4, k = e & 15, n = q0 + ql;
+            sIdx[ql][k] = n < Nd ? (int)a.idx_in[((size_t)b * Nd + n) * LS_KNN_K + k] : 0;
+        }
+    } else {
+        // ------------------------------------------------------------------ phase 1: kNN
+        float(*Qs)[DKC][QT] = reinterpret_cast<float(*)[DKC][QT]>(sbuf);
+        float(*Ss)[DKC][ST] = reinterpret_cast<float(*)[DKC][ST]>(sbuf + 2 * DKC * QT);
+        const float* srcb = a.src_f + (size_t)b * D * Ns;
+        const float* dstb = a.dst_f + (size_t)b * D * Nd;
+        const int n_tiles = (Ns + ST - 1) / ST;
+        const int n_chunks = (D + DKC - 1) / DKC;
+        const int n_it = n_tiles * n_chunks;
+
+        float sreg[DKC], qreg[2];
+        auto g_load = [&](int it) {
+            const int tile = it / n_chunks, chunk = it - tile * n_chunks;
+            const int s = tile * ST + t, d0 = chunk * DKC;
+#pragma unroll
+            for (int dd = 0; dd < DKC; ++dd) {
+                int d = d0 + dd;
+                sreg[dd] = (s < Ns && d < D) ? __ldg(srcb + (size_t)d * Ns + s) : 0.f;
+            }
+            const int q = q0 + (t & 63);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                int d = d0 + (t >> 6) + 4 * i;
+                qreg[i] = (q < Nd && d < D) ? __ldg(dstb + (size_t)d * Nd + q) : 0.f;
+            }
+        };
+        auto s_store = [&](int buf) {
+#pragma unroll
+            for (int dd = 0; dd < DKC; ++dd) Ss[buf][dd][t] = sreg[dd];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) Qs[buf][(t >> 6) + 4 * i][t & 63] = qreg[i];
+        };
+
+        float ld[8], acc[8][8];
+        int li[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ld[i] = FLT_MAX;
+            li[i] = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        }
+
+        g_load(0);
+        s_store(0);
+        __syncthreads();
+        for (int it = 0; it < n_it; ++it) {
+            const int buf = it & 1;
+            if (it + 1 < n_it) g_load(it + 1);
+#pragma unroll
+            for (int dd = 0; dd < DKC; ++dd) {
+                const float4 qa = *reinterpret_cast<const float4*>(&Qs[buf][dd][w * 8]);
+                const float4 qb = *reinterpret_cast<const float4*>(&Qs[buf][dd][w * 8 + 4]);
+                const float4 sa = *reinterpret_cast<const float4*>(&Ss[buf][dd][lane * 4]);
+                const float4 sb = *reinterpret_cast<const float4*>(&Ss[buf][dd][128 + lane * 4]);
+                const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float df = qv[i] - sv[j];
+                        acc[i][j] = fmaf(df, df, acc[i][j]);
+                    }
+            }
+            const int tile = it / n_chunks, chunk = it - tile * n_chunks;
+            if (chunk == n_chunks - 1) {
+                // ---- merge this tile's 8 x (32 x 8) candidates into the running top-16 lists
+                const int sbase = tile * ST + lane * 4;
+#pragma unroll
+                for (int qi = 0; qi < 8; ++qi) {
+                    float tau = __shfl_sync(FULL, ld[qi], 15);
+                    int taui = __shfl_sync(FULL, li[qi], 15);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float d = acc[qi][j];
+                        const int s = sbase + (j < 4 ? j : 124 + j);
+                        const bool ok = (s < Ns) && (d < tau || (d == tau && s < taui));
+                        unsigned m = __ballot_sync(FULL, ok);
+                        while (m) {
+                            const int src = __ffs(m) - 1;
+                            m &= m - 1;
+                            const float cd = __shfl_sync(FULL, d, src);
+                            const int ci = __shfl_sync(FULL, s, src);
+                            if (cd < tau || (cd == tau && ci < taui)) {
+                                topk_insert(ld[qi], li[qi], cd, ci, lane);
+                                tau = __shfl_sync(FULL, ld[qi], 15);
+                                taui = __shfl_sync(FULL, li[qi], 15);
+                            }
+                        }
+                        acc[qi][j] = 0.f;
+                    }
+                }
+            }
+            if (it + 1 < n_it) {
+                s_store(buf ^ 1);
+                __syncthreads();
+            }
+        }
+        if (lane < LS_KNN_K) {
+#pragma unroll
+            for (int qi = 0; qi < 8; ++qi) {
+                sIdx[w * 8 + qi][lane] = li[qi];
+                if (MODE == MODE_KNN_ONLY) sDist[w * 8 + qi][lane] = ld[qi];
+            }
+        }
+    }
+    __syncthreads();
+
+    if (a.idx_out != nullptr) {
+        for (int e = t; e < QT * LS_KNN_K; e += EDGE_THREADS) {
+            int ql = e >> 4, k = e & 15, n = q0 + ql;
+            if (n < Nd) a.idx_out[((size_t)b * Nd + n) * LS_KNN_K + k] = sIdx[ql][k];
+        }
+    }
+    if (MODE == MODE_KNN_ONLY) {
+        if (a.dist_out != nullptr) {
+            for (int e = t; e < QT * LS_KNN_K; e += EDGE_THREADS) {
+                int ql = e >> 4, k = e & 15, n = q0 + ql;
+                if (n < Nd) a.dist_out[((size_t)b * Nd + n) * LS_KNN_K + k] = sDist[ql][k];
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- phase 2: EdgeConv
+    const int Co = a.Co;
+    const float oms = a.oms;
+    const size_t ostride = (size_t)3 * Nd;  // floats between output channels
+
+    if (MODE == MODE_L0) {
+        const float* xyz = a.src_f + (size_t)b * 3 * Ns;  // layer 0: Ns == Nd, src == dst
+        for (int qi = 0; qi < 8; ++qi) {
+            const int ql = w * 8 + qi, n = q0 + ql;
+            if (n >= Nd) break;
+            const float x0 = __ldg(xyz + n), x1 = __ldg(xyz + Ns + n), x2 = __ldg(xyz + 2 * Ns + n);
+            const float nr = fmaxf(sqrtf(fmaf(x2, x2, fmaf(x1, x1, x0 * x0))), EPS_NRM);
+            const float h0 = x0 / nr, h1 = x1 / nr, h2 = x2 / nr;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                const float* wq = a.w0 + (size_t)c * 3;
+                const float* wk = a.w0 + (size_t)(Co + c) * 3;
+                const float wq0 = __ldg(wq), wq1 = __ldg(wq + 1), wq2 = __ldg(wq + 2);
+                const float wk0 = __ldg(wk), wk1 = __ldg(wk + 1), wk2 = __ldg(wk + 2);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    const int m = sIdx[ql][k];
+                    const float n0 = __ldg(xyz + m), n1 = __ldg(xyz + Ns + m), n2 = __ldg(xyz + 2 * Ns + m);
+                    // cross(x_dir, nn)  (vec_dgcnn_atten.py:157)
+                    const float c0 = h1 * n2 - h2 * n1, c1 = h2 * n0 - h0 * n2, c2 = h0 * n1 - h1 * n0;
+                    const float d0 = n0 - x0, d1 = n1 - x1, d2 = n2 - x2;
+                    const float qx = fmaf(wq2, x0, fmaf(wq1, d0, wq0 * c0));
+                    const float qy = fmaf(wq2, x1, fmaf(wq1, d1, wq0 * c1));
+                    const float qz = fmaf(wq2, x2, fmaf(wq1, d2, wq0 * c2));
+                    const float kx = fmaf(wk2, x0, fmaf(wk1, d0, wk0 * c0));
+                    const float ky = fmaf(wk2, x1, fmaf(wk1, d1, wk0 * c1));
+                    const float kz = fmaf(wk2, x2, fmaf(wk1, d2, wk0 * c2));
+                    float o0, o1, o2;
+                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
+                    a0 += o0;
+                    a1 += o1;
+                    a2 += o2;
+                }
+                float* o = a.out + ((size_t)b * Co + c) * ostride + n;
+                o[0] = a0 * (1.f / LS_KNN_K);
+                o[Nd] = a1 * (1.f / LS_KNN_K);
+                o[2 * Nd] = a2 * (1.f / LS_KNN_K);
+            }
+        }
+        return;
+    }
+
+    const float* Ps = a.psrc + (size_t)b * Ns * a.row_s;
+    const int C3 = 3 * Co;  // floats per part
+
+    if (MODE == MODE_MEAN) {
+        for (int qi = 0; qi < 8; ++qi) {
+            const int ql = w * 8 + qi, n = q0 + ql;
+            if (n >= Nd) break;
+            const float* Pd = a.pdst + ((size_t)b * Nd + n) * a.row_d;
+#pragma unroll 1
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                const float dq0 = __ldg(Pd + c), dq1 = __ldg(Pd + Co + c), dq2 = __ldg(Pd + 2 * Co + c);
+                const float dk0 = __ldg(Pd + C3 + c), dk1 = __ldg(Pd + C3 + Co + c), dk2 = __ldg(Pd + C3 + 2 * Co + c);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + c;
+                    const float qx = __ldg(row) + dq0, qy = __ldg(row + Co) + dq1, qz = __ldg(row + 2 * Co) + dq2;
+                    const float kx = __ldg(row + C3) + dk0, ky = __ldg(row + C3 + Co) + dk1,
+                                kz = __ldg(row + C3 + 2 * Co) + dk2;
+                    float o0, o1, o2;
+                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
+                    a0 += o0;
+                    a1 += o1;
+                    a2 += o2;
+                }
+                float* o = a.out + ((size_t)b * Co + c) * ostride + n;
+                o[0] = a0 * (1.f / LS_KNN_K);
+                o[Nd] = a1 * (1.f / LS_KNN_K);
+                o[2 * Nd] = a2 * (1.f / LS_KNN_K);
+            }
+        }
+        return;
+    }
+
+    if (MODE == MODE_ATT) {
+        float* sR = sbuf + (size_t)w * CPL * 32;  // [CPL][32] per warp (phase-1 tiles are dead)
+        const float inv_sqrt = rsqrtf(3.f * (float)LS_HEAD_C);
+        for (int qi = 0; qi < 8; ++qi) {
+            const int ql = w * 8 + qi, n = q0 + ql;
+            if (n >= Nd) break;
+            const float* Pd = a.pdst + ((size_t)b * Nd + n) * a.row_d;
+            // ---- |Q|: channel-norm of the activated query feature (cevn, vec_layers.py:24-31)
+            float ssum = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                const float* pq = Pd + 4 * C3 + c;
+                float o0, o1, o2;
+                vn_act(__ldg(pq), __ldg(pq + Co), __ldg(pq + 2 * Co), __ldg(pq + C3), __ldg(pq + C3 + Co),
+                       __ldg(pq + C3 + 2 * Co), oms, o0, o1, o2);
+                ssum += fmaf(o2, o2, fmaf(o1, o1, o0 * o0));
+            }
+            ssum = warp_sum(ssum);
+            const float Lq = fmaxf(sqrtf(ssum), EPS_NRM);
+
+            // ---- pass A: K branch -> per-edge channel norm and per-head raw logits
+            float S[LS_KNN_K];
+#pragma unroll
+            for (int k = 0; k < LS_KNN_K; ++k) S[k] = 0.f;
+#pragma unroll 1
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                const float* pq = Pd + 4 * C3 + c;
+                float v0, v1, v2;
+                vn_act(__ldg(pq), __ldg(pq + Co), __ldg(pq + 2 * Co), __ldg(pq + C3), __ldg(pq + C3 + Co),
+                       __ldg(pq + C3 + 2 * Co), oms, v0, v1, v2);
+                const float ell = sqrtf(fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
+                const float ed = fmaxf(ell, EPS_NRM), fn = ell / Lq;
+                const float g0 = (v0 / ed) * fn, g1 = (v1 / ed) * fn, g2 = (v2 / ed) * fn;  // cevn(Q)
+                const float* pk = Pd + 2 * C3 + c;
+                const float dq0 = __ldg(pk), dq1 = __ldg(pk + Co), dq2 = __ldg(pk + 2 * Co);
+                const float dk0 = __ldg(pk + C3), dk1 = __ldg(pk + C3 + Co), dk2 = __ldg(pk + C3 + 2 * Co);
+                float Rj = 0.f;
+#pragma unroll
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + 2 * C3 + c;
+                    const float qx = __ldg(row) + dq0, qy = __ldg(row + Co) + dq1, qz = __ldg(row + 2 * Co) + dq2;
+                    const float kx = __ldg(row + C3) + dk0, ky = __ldg(row + C3 + Co) + dk1,
+                                kz = __ldg(row + C3 + 2 * Co) + dk2;
+                    float o0, o1, o2;
+                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
+                    S[k] += fmaf(o2, o2, fmaf(o1, o1, o0 * o0));
+                    float r = fmaf(o2, g2, fmaf(o1, g1, o0 * g0));
+                    r = half_sum(r);
+                    if ((lane & 15) == k) Rj = r;
+                }
+                sR[j * 32 + lane] = Rj;
+            }
+            float Sme = 0.f;
+#pragma unroll
+            for (int k = 0; k < LS_KNN_K; ++k) {
+                const float s = warp_sum(S[k]);
+                if ((lane & 15) == k) Sme = s;
+            }
+            const float Lk = fmaxf(sqrtf(Sme), EPS_NRM);
+            __syncwarp();
+#pragma unroll 1
+            for (int j = 0; j < CPL; ++j) {
+                const float logit = (sR[j * 32 + lane] / Lk) * inv_sqrt;
+                const float mx = half_max(logit);
+                const float e = expf(logit - mx);
+                const float den = half_sum(e);
+                sR[j * 32 + lane] = e / den;
+            }
+            __syncwarp();
+            // ---- pass B: V branch, attention-weighted sum over the 16 edges
+#pragma unroll 1
+            for (int j = 0; j < CPL; ++j) {
+                const int c = j * 32 + lane;
+                const float al = sR[j * 32 + lane];
+                const float dq0 = __ldg(Pd + c), dq1 = __ldg(Pd + Co + c), dq2 = __ldg(Pd + 2 * Co + c);
+                const float dk0 = __ldg(Pd + C3 + c), dk1 = __ldg(Pd + C3 + Co + c), dk2 = __ldg(Pd + C3 + 2 * Co + c);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    const float ak = __shfl_sync(FULL, al, (lane & 16) | k);
+                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + c;
+                    const float qx = __ldg(row) + dq0, qy = __ldg(row + Co) + dq1, qz = __ldg(row + 2 * Co) + dq2;
+                    const float kx = __ldg(row + C3) + dk0, ky = __ldg(row + C3 + Co) + dk1,
+                                kz = __ldg(row + C3 + 2 * Co) + dk2;
+                    float o0, o1, o2;
+                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
+                    a0 = fmaf(ak, o0, a0);
+                    a1 = fmaf(ak, o1, a1);
+                    a2 = fmaf(ak, o2, a2);
+                }
+                float* o = a.out + ((size_t)b * Co + c) * ostride + n;
+                o[0] = a0;
+                o[Nd] = a1;
+                o[2 * Nd] = a2;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ============================================================================================
+// Global context (vec_dgcnn_atten.py:222-225): g = mean_n f ; bias[r][a] = sum_c Wg2[r][c] g[c][a]
+// so that VecLNA_G([f ; g]) = Wg1 f + bias.  One CTA per instance.
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_mean_bias(const float* __restrict__ f, int Co, int Nd,
+                                                   const float* __restrict__ wg2, float* __restrict__ bias) {
+    extern __shared__ float sg[];  // [Co*3]
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const float* fb = f + (size_t)b * Co * 3 * Nd;
+    for (int r = w; r < Co * 3; r += 8) {
+        float s = 0.f;
+        for (int n = lane; n < Nd; n += 32) s += fb[(size_t)r * Nd + n];
+        s = warp_sum(s);
+        if (lane == 0) sg[r] = s / (float)Nd;
+    }
+    __syncthreads();
+    for (int r = w; r < 2 * Co; r += 8) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int c = lane; c < Co; c += 32) {
+            float wv = __ldg(wg2 + (size_t)r * Co + c);
+            s0 = fmaf(wv, sg[c * 3 + 0], s0);
+            s1 = fmaf(wv, sg[c * 3 + 1], s1);
+            s2 = fmaf(wv, sg[c * 3 + 2], s2);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            float* o = bias + ((size_t)b * 2 * Co + r) * 3;
+            o[0] = s0;
+            o[1] = s1;
+            o[2] = s2;
+        }
+    }
+}
+
+// raw [B][2Co][3][N] (q rows, then direction rows) -> VN leaky-ReLU -> out [B][Co][3][N]
+__global__ void k_vnact(const float* __restrict__ raw, int Co, int N, float oms, float* __restrict__ out) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* q = raw + ((size_t)b * 2 * Co + c) * 3 * N + n;
+    const float* k = raw + ((size_t)b * 2 * Co + Co + c) * 3 * N + n;
+    float o0, o1, o2;
+    vn_act(q[0], q[N], q[2 * N], k[0], k[N], k[2 * N], oms, o0, o1, o2);
+    float* o = out + ((size_t)b * Co + c) * 3 * N + n;
+    o[0] = o0;
+    o[N] = o1;
+    o[2 * N] = o2;
+}
+
+// ============================================================================================
+// Head (vec_dgcnn_atten.py:231-252 + VecResBlock vec_layers.py:631-672): one CTA per instance,
+// blockDim = c_dim, thread c owns channel c.
+// ============================================================================================
+struct HeadArgs {
+    const float* raw;  // [B][c_dim+1][3][Nl]  conv_c pre-activation rows + shared direction row
+    int c_dim, Nl;
+    const float* w_inv_t;
+    const float* w_fc0_t;
+    const float* w_lin1;
+    const float* w_short;
+    float w_act2, oms, scale_factor;
+    int center_pred, center_pred_scale, normalize;
+    const float* centroid;  // [B][3]  (normalize)
+    const float* s0;        // [B]
+    float *center, *scale, *z_so3, *z_inv, *packed;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red, int nw) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    return s;
+}
+
+__global__ void __launch_bounds__(1024) k_head(const HeadArgs a) {
+    extern __shared__ float sm[];
+    const int C = a.c_dim, Nl = a.Nl;
+    float* sx = sm;          // [C][3]
+    float* sf = sm + 3 * C;  // [C][3]  fc0 outputs (q cols then k cols)
+    __shared__ float red[32];
+    const int b = blockIdx.x, c = threadIdx.x, nw = blockDim.x >> 5;
+    const float* rb = a.raw + (size_t)b * (C + 1) * 3 * Nl;
+    const float* q = rb + (size_t)c * 3 * Nl;
+    const float* kd = rb + (size_t)C * 3 * Nl;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    for (int n = 0; n < Nl; ++n) {
+        float o0, o1, o2;
+        vn_act(q[n], q[Nl + n], q[2 * Nl + n], kd[n], kd[Nl + n], kd[2 * Nl + n], a.oms, o0, o1, o2);
+        x0 += o0;
+        x1 += o1;
+        x2 += o2;
+    }
+    x0 /= (float)Nl;
+    x1 /= (float)Nl;
+    x2 /= (float)Nl;
+    sx[c * 3 + 0] = x0;
+    sx[c * 3 + 1] = x1;
+    sx[c * 3 + 2] = x2;
+    const float ell = sqrtf(fmaf(x2, x2, fmaf(x1, x1, x0 * x0)));
+    const float L = fmaxf(sqrtf(block_sum(ell * ell, red, nw)), EPS_NRM);
+    const float sc_sum = block_sum(ell, red, nw);  // also orders the sx writes before the reads below
+    const float ed = fmaxf(ell, EPS_NRM), fn = ell / L;
+    const float z0 = (x0 / ed) * fn, z1 = (x1 / ed) * fn, z2 = (x2 / ed) * fn;  // z_so3 = cevn(x)
+    float pred_scale = (sc_sum / (float)C) * a.scale_factor;
+
+    // z_inv: <cevn(fc_inv x)[c], z_so3[c]>
+    float u0 = 0.f, u1 = 0.f, u2 = 0.f;
+    for (int k = 0; k < C; ++k) {
+        const float wv = __ldg(a.w_inv_t + (size_t)k * C + c);
+        u0 = fmaf(wv, sx[k * 3 + 0], u0);
+        u1 = fmaf(wv, sx[k * 3 + 1], u1);
+        u2 = fmaf(wv, sx[k * 3 + 2], u2);
+    }
+    const float ul = sqrtf(fmaf(u2, u2, fmaf(u1, u1, u0 * u0)));
+    const float UL = fmaxf(sqrtf(block_sum(ul * ul, red, nw)), EPS_NRM);
+    const float ud = fmaxf(ul, EPS_NRM), un = ul / UL;
+    const float zi = ((u0 / ud) * un) * z0 + ((u1 / ud) * un) * z1 + ((u2 / ud) * un) * z2;
+
+    float ctr[3] = {0.f, 0.f, 0.f};
+    if (a.center_pred) {
+        // fc0 = VecLNA(C -> C/2): column c < C/2 is q_c, column C/2 + o is the direction of channel o
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+        for (int k = 0; k < C; ++k) {
+            const float wv = __ldg(a.w_fc0_t + (size_t)k * C + c);
+            f0 = fmaf(wv, sx[k * 3 + 0], f0);
+            f1 = fmaf(wv, sx[k * 3 + 1], f1);
+            f2 = fmaf(wv, sx[k * 3 + 2], f2);
+        }
+        sf[c * 3 + 0] = f0;
+        sf[c * 3 + 1] = f1;
+        sf[c * 3 + 2] = f2;
+        __syncthreads();
+        const int h = C / 2;
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+        if (c < h) {
+            float o0, o1, o2;
+            vn_act(sf[c * 3], sf[c * 3 + 1], sf[c * 3 + 2], sf[(h + c) * 3], sf[(h + c) * 3 + 1], sf[(h + c) * 3 + 2],
+                   a.oms, o0, o1, o2);
+            const float w1 = __ldg(a.w_lin1 + c);
+            d0 = w1 * o0;
+            d1 = w1 * o1;
+            d2 = w1 * o2;
+        }
+        const float ws = __ldg(a.w_short + c);
+        const float v0 = block_sum(fmaf(ws, x0, d0), red, nw);
+        const float v1 = block_sum(fmaf(ws, x1, d1), red, nw);
+        const float v2 = block_sum(fmaf(ws, x2, d2), red, nw);
+        vn_act(v0, v1, v2, a.w_act2 * v0, a.w_act2 * v1, a.w_act2 * v2, a.oms, ctr[0], ctr[1], ctr[2]);
+        if (a.center_pred_scale) {
+            ctr[0] *= a.scale_factor;
+            ctr[1] *= a.scale_factor;
+            ctr[2] *= a.scale_factor;
+        }
+    }
+    if (a.normalize) {  // model_utils.py:182-185
+        pred_scale = a.s0[b] * pred_scale;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ctr[i] += a.centroid[b * 3 + i];
+    }
+    float* zs = a.z_so3 + ((size_t)b * C + c) * 3;
+    zs[0] = z0;
+    zs[1] = z1;
+    zs[2] = z2;
+    a.z_inv[(size_t)b * C + c] = zi;
+    if (a.packed) {
+        float* p = a.packed + (size_t)b * (4 * C + 4);
+        p[c * 3 + 0] = z0;
+        p[c * 3 + 1] = z1;
+        p[c * 3 + 2] = z2;
+        p[3 * C + c] = zi;
+    }
+    if (c == 0) {
+        a.scale[b] = pred_scale;
+        if (a.center) {
+            a.center[b * 3 + 0] = ctr[0];
+            a.center[b * 3 + 1] = ctr[1];
+            a.center[b * 3 + 2] = ctr[2];
+        }
+        if (a.packed) {
+            float* p = a.packed + (size_t)b * (4 * C + 4) + 4 * C;
+            p[0] = pred_scale;
+            p[1] = ctr[0];
+            p[2] = ctr[1];
+            p[3] = ctr[2];
+        }
+    }
+}
+
+}  // namespace ls

@@ -1,0 +1,160 @@
+"""DeepSDF decoder + FieldWrapper -- drop-ins for the reference's SDF query path.
+
+Mirrors ``lib_shape_prior/core/lib/implicit_func/deepsdf_decoder.py:9-123`` (parameter names
+``lin{0..7}.{bias,weight_g,weight_v}``, ``lin8.{weight,bias}``) and ``model_utils.py:221-263``
+(``FieldWrapper.forward(query, z_none, c, return_sdf=False)``, ``inner_deepsdf`` branch).
+The modules hold parameters; the arithmetic runs in ``ls_sdf_decode`` (C ABI).
+Inference only: back-propagation through the decoder (the reference's ``optim=True`` registration
+and ``_optimize_code``, more_solver.py:118-228) is out of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import distributions as dist
+from torch import nn
+
+from . import _lib
+
+
+class _WNLinear(nn.Module):
+    """Parameters of ``nn.utils.weight_norm(nn.Linear(i, o))``: bias, weight_g [o,1], weight_v [o,i]."""
+
+    def __init__(self, i: int, o: int):
+        super().__init__()
+        lin = nn.Linear(i, o)
+        self.bias = nn.Parameter(lin.bias.detach().clone())
+        self.weight_g = nn.Parameter(lin.weight.detach().norm(dim=1, keepdim=True))
+        self.weight_v = nn.Parameter(lin.weight.detach().clone())
+
+    def effective(self):
+        return torch._weight_norm(self.weight_v.detach(), self.weight_g.detach(), 0), self.bias.detach()
+
+
+class _Linear(nn.Module):
+    def __init__(self, i: int, o: int):
+        super().__init__()
+        lin = nn.Linear(i, o)
+        self.weight = nn.Parameter(lin.weight.detach().clone())
+        self.bias = nn.Parameter(lin.bias.detach().clone())
+
+    def effective(self):
+        return self.weight.detach(), self.bias.detach()
+
+
+class DeepSDF_Decoder(nn.Module):
+    def __init__(self, latent_size, dims, dropout=None, dropout_prob=0.0, norm_layers=(), latent_in=(),
+                 weight_norm=False, xyz_in_all=None, use_tanh=False, latent_dropout=False, pe_dim=3):
+        super().__init__()
+        if xyz_in_all or use_tanh or latent_dropout:
+            raise NotImplementedError("only the shipped decoder configuration is built")
+        full = [latent_size + pe_dim] + list(dims) + [1]
+        self.latent_size, self.pe_dim = latent_size, pe_dim
+        self.num_layers = len(full)
+        self.latent_in = list(latent_in)
+        self.in_dims, self.out_dims = [], []
+        for layer in range(self.num_layers - 1):
+            out_dim = full[layer + 1] - full[0] if layer + 1 in self.latent_in else full[layer + 1]
+            wn = weight_norm and layer in list(norm_layers)
+            setattr(self, f"lin{layer}", (_WNLinear if wn else _Linear)(full[layer], out_dim))
+            self.in_dims.append(full[layer])
+            self.out_dims.append(out_dim)
+        if self.num_layers - 1 != 9 or self.latent_in != [4] or pe_dim != latent_size + 1:
+            raise NotImplementedError("ls_sdf_decode is built for the shipped 9-layer inner_deepsdf decoder "
+                                      "(latent_in=[4], pe_dim=latent_size+1)")
+        self._packed: Optional[dict] = None
+
+    def _pack(self, device) -> dict:
+        ver = (tuple((p.data_ptr(), p._version) for p in self.parameters()), str(device))
+        if self._packed is not None and self._packed["ver"] == ver:
+            return self._packed
+        L, H = self.latent_size, self.out_dims[0]
+        arrays = {}
+        eff = [getattr(self, f"lin{l}").effective() for l in range(9)]
+        W0, W4 = eff[0][0].float().cpu(), eff[4][0].float().cpu()
+        h3 = self.out_dims[3]
+        arrays["w0_zinv"] = W0[:, :L]
+        arrays["w4_zinv"] = W4[:, h3:h3 + L]
+        mats = {0: W0[:, L:], 4: torch.cat([W4[:, :h3], W4[:, h3 + L:]], 1)}
+        for l in range(9):
+            W = mats.get(l, eff[l][0].float().cpu())
+            K = W.shape[1]
+            Kp = (K + 7) // 8 * 8
+            Wp = torch.zeros(W.shape[0], Kp)
+            Wp[:, :K] = W
+            arrays[f"w{l}"] = Wp
+            arrays[f"b{l}"] = eff[l][1].float().cpu()
+        offs, total = {}, 0
+        for k, v in arrays.items():
+            offs[k] = total
+            total += (v.numel() + 63) // 64 * 64
+        blob = torch.zeros(total, dtype=torch.float32)
+        for k, v in arrays.items():
+            blob[offs[k]:offs[k] + v.numel()] = v.reshape(-1)
+        blob = blob.to(device)
+        base = blob.data_ptr()
+        d = _lib.DecoderDesc()
+        d.latent, d.hidden, d.n_layers, d.latent_in = L, H, 9, 4
+        for l in range(9):
+            d.w[l] = base + 4 * offs[f"w{l}"]
+            d.b[l] = base + 4 * offs[f"b{l}"]
+            d.out_dims[l] = self.out_dims[l]
+            d.in_dims[l] = mats[l].shape[1] if l in mats else self.in_dims[l]
+        d.w0_zinv = base + 4 * offs["w0_zinv"]
+        d.w4_zinv = base + 4 * offs["w4_zinv"]
+        self._packed = {"ver": ver, "blob": blob, "desc": d}
+        return self._packed
+
+    @torch.no_grad()
+    def query(self, query: torch.Tensor, code: dict) -> torch.Tensor:
+        """query [B,M,3] world coordinates + code dict -> sdf [B,M] (tanh output)."""
+        _lib.require_cuda(query, "query")
+        dev = query.device
+        q = query.detach().float().contiguous()
+        B, M, _ = q.shape
+        z_so3 = code["z_so3"].detach().float().contiguous()
+        z_inv = code["z_inv"].detach().float().contiguous()
+        s = code["s"].detach().float().reshape(B).contiguous()
+        t = code["t"].detach().float().reshape(B, 3).contiguous()
+        assert z_so3.shape == (B, self.latent_size, 3) and z_inv.shape == (B, self.latent_size)
+        with torch.cuda.device(dev):
+            pk = self._pack(dev)
+            nbytes = C.c_size_t(0)
+            _lib.check(_lib.lib().ls_sdf_workspace_bytes(C.byref(pk["desc"]), B, M, C.byref(nbytes)),
+                       "ls_sdf_workspace_bytes")
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            sdf = torch.empty(B, M, device=dev)
+            rc = _lib.lib().ls_sdf_decode(C.byref(pk["desc"]), q.data_ptr(), z_so3.data_ptr(), z_inv.data_ptr(),
+                                          s.data_ptr(), t.data_ptr(), B, M, sdf.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), _lib.stream_ptr(dev))
+            _lib.check(rc, "ls_sdf_decode")
+            _lib.launch_count += 1
+            ws.record_stream(torch.cuda.current_stream(dev))
+        return sdf
+
+    def forward(self, input, phase="val"):
+        raise NotImplementedError(
+            "the CUDA decoder never materialises the [B,M,513] input tensor; call FieldWrapper.forward "
+            "(query, None, code, return_sdf) as the reference's callers do (model_utils.py:230-263)")
+
+
+class FieldWrapper(nn.Module):
+    """model_utils.py:221-263 (inner_deepsdf branch)."""
+
+    def __init__(self, decoder, decoder_type="inner_deepsdf", sdf2occ_factor=-1.0) -> None:
+        super().__init__()
+        if decoder_type != "inner_deepsdf":
+            raise NotImplementedError("only decoder_type == 'inner_deepsdf' (the shipped model) is built")
+        self.F = decoder
+        self.sdf2occ_factor = sdf2occ_factor
+        self.decoder_type = decoder_type
+
+    def forward(self, query, z_none, c, return_sdf=False):
+        if any(torch.is_tensor(v) and v.requires_grad for v in (query, *c.values())) and torch.is_grad_enabled():
+            raise NotImplementedError("the CUDA SDF decoder is inference-only (no backward); see SURVEY.md 8f rank 4")
+        sdf = self.F.query(query, c).to(query.dtype)
+        if return_sdf:
+            return sdf
+        return dist.Bernoulli(logits=self.sdf2occ_factor * sdf)

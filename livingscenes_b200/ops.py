@@ -1,0 +1,77 @@
+"""Stand-alone graph ops at the reference's pytorch3d boundary, executed by the CUDA library.
+
+  knn_points              pytorch3d.ops.knn.knn_points as called at vec_dgcnn_atten.py:139-141
+  sample_farthest_points  pytorch3d.ops.sample_farthest_points (vec_dgcnn_atten.py:169,
+                          model_utils.py:205, more_solver.py:67,107-108)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+@torch.no_grad()
+def knn_points(p1: torch.Tensor, p2: torch.Tensor, K: int = 16, return_nn: bool = False):
+    """p1 [B,P1,D], p2 [B,P2,D] -> (dists [B,P1,K] squared L2, idx [B,P1,K] int64, nn | None).
+    Ascending distance; ties resolved towards the lower p2 index."""
+    if K != _lib.LS_KNN_K:
+        raise NotImplementedError("ls_knn is built for K == 16 (num_knn of the shipped model)")
+    _lib.require_cuda(p1, "p1")
+    B, P1, D = p1.shape
+    P2 = p2.shape[1]
+    q = p1.detach().float().transpose(1, 2).contiguous()  # [B,D,P1] channel-major
+    s = p2.detach().float().transpose(1, 2).contiguous()
+    idx = torch.empty(B, P1, K, dtype=torch.int64, device=p1.device)
+    d2 = torch.empty(B, P1, K, dtype=torch.float32, device=p1.device)
+    with torch.cuda.device(p1.device):
+        rc = _lib.lib().ls_knn(q.data_ptr(), s.data_ptr(), B, D, P1, P2, idx.data_ptr(), d2.data_ptr(),
+                               _lib.stream_ptr(p1.device))
+        _lib.check(rc, "ls_knn")
+        _lib.launch_count += 1
+    nn = None
+    if return_nn:
+        nn = torch.gather(p2[:, None].expand(B, P1, P2, D), 2, idx[..., None].expand(B, P1, K, D))
+    return d2, idx, nn
+
+
+@torch.no_grad()
+def knn_graph_cm(query_cm: torch.Tensor, source_cm: torch.Tensor):
+    """Channel-major variant: query [B,D,Nq], source [B,D,Ns] -> (idx [B,Nq,16] int64, dist2)."""
+    _lib.require_cuda(query_cm, "query")
+    B, D, Nq = query_cm.shape
+    Ns = source_cm.shape[2]
+    q = query_cm.detach().float().contiguous()
+    s = source_cm.detach().float().contiguous()
+    idx = torch.empty(B, Nq, _lib.LS_KNN_K, dtype=torch.int64, device=q.device)
+    d2 = torch.empty(B, Nq, _lib.LS_KNN_K, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().ls_knn(q.data_ptr(), s.data_ptr(), B, D, Nq, Ns, idx.data_ptr(), d2.data_ptr(),
+                               _lib.stream_ptr(q.device))
+        _lib.check(rc, "ls_knn")
+        _lib.launch_count += 1
+    return idx, d2
+
+
+@torch.no_grad()
+def farthest_point_sample(xyz_cm: torch.Tensor, n_out: int):
+    """xyz [B,3,N] (channel-major) -> (idx [B,n_out] int64, sampled xyz [B,3,n_out]); start index 0."""
+    _lib.require_cuda(xyz_cm, "xyz")
+    B, three, N = xyz_cm.shape
+    assert three == 3
+    x = xyz_cm.detach().float().contiguous()
+    idx = torch.empty(B, n_out, dtype=torch.int64, device=x.device)
+    out = torch.empty(B, 3, n_out, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ls_fps(x.data_ptr(), B, N, n_out, idx.data_ptr(), out.data_ptr(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "ls_fps")
+        _lib.launch_count += 1
+    return idx, out
+
+
+def sample_farthest_points(points: torch.Tensor, K: int = 50, random_start_point: bool = False):
+    """pytorch3d signature: points [B,P,3] -> (pts [B,K,3], idx [B,K])."""
+    if random_start_point:
+        raise NotImplementedError("random_start_point is not built (the evals use n_init = 1, start index 0)")
+    idx, out = farthest_point_sample(points.transpose(1, 2), K)
+    return out.transpose(1, 2).to(points.dtype), idx

@@ -1,0 +1,105 @@
+"""CPU: the oracle restatement against the committed golden vectors (generated from the reference's
+own modules by oracle/make_golden.py), and against the reference itself where it is mounted."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, relerr, state_dict_for
+from oracle import p3d_shim
+from oracle import restatement as R
+
+
+@pytest.mark.parametrize("tag", ["random", "shipped"])
+def test_restatement_encoder_matches_golden(tag):
+    sd = state_dict_for(tag)
+    g = golden(f"encoder_{tag}")
+    x = torch.from_numpy(g["x"])[:1]  # one instance keeps the CPU suite short
+    tr = {}
+    with torch.no_grad():
+        code = R.encode(sd, x, trace=tr)
+    for i in range(7):
+        assert np.array_equal(tr["knn_idx"][i].numpy(), g[f"knn_idx_{i}"][:1].astype(np.int64)), f"kNN layer {i}"
+    for i in range(3):
+        assert np.array_equal(tr["fps_idx"][i].numpy(), g[f"fps_idx_{i}"][:1].astype(np.int64)), f"FPS call {i}"
+    assert relerr(tr["scale0"], g["scale0"][:1]) < 1e-6
+    for k, gk in (("z_so3", "enc_z_so3"), ("z_inv", "enc_z_inv"), ("s", "enc_s"), ("t", "enc_t")):
+        assert relerr(code[k], g[gk][:1]) < 2e-5, k
+    for i in range(7):
+        assert relerr(tr["feat"][i][..., ::16], g[f"feat_{i}"][:1]) < 2e-5
+
+
+def test_restatement_solvers_match_golden():
+    g = golden("solver_cases")
+    for ci in range(int(g["n_match_cases"])):
+        z0, z1 = torch.from_numpy(g[f"m{ci}_z0"]), torch.from_numpy(g[f"m{ci}_z1"])
+        r = R.sequential_match(z0, z1)
+        assert np.array_equal(r["matches0"].numpy(), g[f"m{ci}_seq0"]), ci
+        assert np.array_equal(r["matches1"].numpy(), g[f"m{ci}_seq1"]), ci
+        rn = R.mutual_nn_match(z0.T[None], z1.T[None])
+        assert np.array_equal(rn["matches0"].reshape(-1).numpy(), g[f"m{ci}_nn0"]), ci
+        assert np.array_equal(rn["matches1"].reshape(-1).numpy(), g[f"m{ci}_nn1"]), ci
+    x1, x2, w = (torch.from_numpy(g[k]) for k in ("k_x1", "k_x2", "k_w"))
+    Rm, tm, res = R.kabsch(x1, x2)
+    assert float((Rm - torch.from_numpy(g["k_R"])).abs().max()) < 1e-4
+    assert float((tm - torch.from_numpy(g["k_t"])).abs().max()) < 1e-4
+    assert float((res - torch.from_numpy(g["k_res"])).abs().max()) < 1e-4
+    Rw, tw, _ = R.kabsch(x1, x2, weights=w)
+    assert float((Rw - torch.from_numpy(g["k_Rw"])).abs().max()) < 1e-4
+    # proper rotations, including the mirrored-target case (det fix)
+    assert torch.allclose(torch.det(Rm), torch.ones(Rm.shape[0]), atol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["random", "shipped"])
+def test_restatement_sdf_matches_golden(tag):
+    sd = state_dict_for(tag)
+    g = golden(f"sdf_{tag}")
+    code = {k: torch.from_numpy(g[k]) for k in ("z_so3", "z_inv", "s", "t")}
+    with torch.no_grad():
+        sdf = R.sdf_decode(sd, torch.from_numpy(g["query"]), code)
+    assert float((sdf - torch.from_numpy(g["sdf"])).abs().max()) < 1e-5
+
+
+def test_shim_knn_ties_and_order():
+    # duplicates => exact ties: lower index first, ascending distances, self first
+    p = torch.tensor([[[0., 0, 0], [1, 0, 0], [1, 0, 0], [0, 2, 0], [0, -2, 0]]])
+    d, idx, _ = p3d_shim.knn_points(p, p, K=4)
+    assert idx[0, 0].tolist() == [0, 1, 2, 3]
+    assert idx[0, 1].tolist()[:2] == [1, 2] and idx[0, 2].tolist()[:2] == [1, 2]
+    assert torch.all(d[0, :, 1:] >= d[0, :, :-1])
+
+
+def test_shim_fps_known_answer():
+    # collinear points: FPS from index 0 picks the far end, then the middle-most
+    x = torch.tensor([[[0.0, 0, 0], [1, 0, 0], [2, 0, 0], [3, 0, 0], [10, 0, 0]]])
+    _, idx = p3d_shim.sample_farthest_points(x, K=3)
+    assert idx[0].tolist() == [0, 4, 3]
+    # ties -> lowest index
+    x = torch.tensor([[[0.0, 0, 0], [1, 0, 0], [-1, 0, 0], [0, 1, 0]]])
+    _, idx = p3d_shim.sample_farthest_points(x, K=2)
+    assert idx[0].tolist() == [0, 1]
+
+
+def test_scale0_quirk():
+    # top-5 of the flattened symmetric matrix = (2 d1 + 2 d2 + d3) / 5
+    x = R.synth_instances(1, 128, 7)
+    xc = x - x.mean(-1, keepdim=True)
+    d = torch.cdist(xc.transpose(1, 2), xc.transpose(1, 2))[0]
+    iu = torch.triu_indices(128, 128, 1)
+    top = d[iu[0], iu[1]].topk(3)[0]
+    expect = (2 * top[0] + 2 * top[1] + top[2]) / 5
+    assert abs(float(R.scale0(xc)[0]) - float(expect)) < 1e-6
+
+
+def test_reference_modules_agree_with_restatement_when_mounted():
+    from oracle import ref_loader
+
+    if not (ref_loader.available() and ref_loader.checkpoint_available()):
+        pytest.skip("/root/reference not mounted")
+    sd = R.random_state_dict(0)
+    sp = ref_loader.shape_prior(sd)
+    x = R.synth_instances(1, 512, 99)
+    with torch.no_grad():
+        ref = sp.encode(x)
+        mine = R.encode(sd, x)
+    for k in ref:
+        assert relerr(mine[k], ref[k]) < 2e-5, k
