@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LivingScenes hot path on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+metric   instances/sec (N=1024 points) for encode + match + pose
+step     one pass over one batch of synthetic input PER GPU: 4 scene pairs x (32 ref + 32 rescan
+         instances) = 256 instances of 1024 points (BASELINE config[1] batch, C3-style pairs):
+         Shape_Prior.encode of all 256 -> [N>1: one NCCL all-gather of the packed 1028-float codes] ->
+         sequential_matcher per pair -> Kabsch SE(3) per matched ref instance.
+value    whole-job instances/s with inputs resident in HBM (CUDA events around every step, L2 flushed
+         between steps, max over ranks).
+e2e      the same through the public API from PINNED HOST buffers: H2D of the clouds and D2H of
+         matches / R / t inside the timed region.
+roofline the fused kNN+EdgeConv launch with the largest share, timed live with CUDA events on the
+         launching stream (ls_profile_* hooks of the C ABI), against MEASURED_PEAKS.json.
+--impl reference  times the CPU restatement of the reference path (oracle/, kind "port"; the Python
+         reference itself cannot travel to the GPU box) on the host cores, same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_POINTS = 1024
+PAIRS_PER_GPU = 4
+INST_PER_SET = 32
+INST_PER_GPU = PAIRS_PER_GPU * 2 * INST_PER_SET  # 256
+N_INPUT_SETS = 4
+SHIPPED = os.path.join(ROOT, "livingscenes_b200", "_weights", "shipped_fp32.pt")
+FEAT = [32, 32, 64, 64, 128, 256, 512]
+DOWN = {2: 2, 4: 4, 5: 4}
+
+
+def load_state_dict():
+    from oracle import restatement as R  # only for the seeded stand-in weights / synthetic clouds
+
+    if os.path.exists(SHIPPED):
+        return torch.load(SHIPPED, map_location="cpu", weights_only=True), "shipped checkpoint weights"
+    return R.random_state_dict(0), "seeded random weights (shipped checkpoint not present)"
+
+
+def make_scene_batch(n_pairs: int, seed: int):
+    """[n_pairs*64, 3, 1024]: per pair 32 ref instances then 32 rescan instances = permuted, rotated,
+    translated, re-noised copies of the ref ones (SURVEY.md 8d, config C3 at N=1024)."""
+    from oracle import restatement as R
+
+    g = torch.Generator().manual_seed(seed)
+    out, perms = [], []
+    for p in range(n_pairs):
+        ref = R.synth_instances(INST_PER_SET, N_POINTS, seed * 1000 + p)
+        perm = torch.randperm(INST_PER_SET, generator=g)
+        Rg = R.random_rotations(INST_PER_SET, seed * 1000 + 500 + p)
+        tg = torch.randn(INST_PER_SET, 3, 1, generator=g)
+        res = Rg @ ref[perm] + tg + 0.002 * torch.randn(INST_PER_SET, 3, N_POINTS, generator=g)
+        out += [ref, res]
+        perms.append(perm)
+    return torch.cat(out, 0).contiguous(), perms
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- roofline
+def layer_geometry(N: int):
+    geo, n = [], N
+    for i, co in enumerate(FEAT):
+        ns = n
+        n //= DOWN.get(i, 1)
+        geo.append(dict(layer=i, c_in=1 if i == 0 else FEAT[i - 1], c_out=co, n_src=ns, n_dst=n))
+    return geo
+
+
+def knn_edge_algorithmic(g: dict):
+    """Per instance, SURVEY.md 8d: bytes = 4*C_in*3*N_src + 4*C_out*3*N_dst + 8*N_dst*K;
+    FLOPs = 3*N_dst*N_src*3*C_in (kNN) + the layer's reference-form VN FLOPs (edge-level V[,K] branches:
+    2*(2C_in)*C_out*3*N_dst*K for lin + 2*C_out^2*3*N_dst*K for lin_dir, per branch)."""
+    ci, co, ns, nd = g["c_in"], g["c_out"], g["n_src"], g["n_dst"]
+    byt = 4 * ci * 3 * ns + 4 * co * 3 * nd + 8 * nd * 16
+    knn = 3 * nd * ns * 3 * ci
+    cg = 3 if g["layer"] == 0 else 2 * ci
+    branches = 1 if g["layer"] < 2 else 2
+    vn = branches * (2 * cg * co + 2 * co * co) * 3 * nd * 16
+    return byt, knn + vn
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_path_step(sd, x_pair, use_reference_modules):
+    """encode + sequential match + Kabsch of one small scene pair on the host cores."""
+    from oracle import restatement as R
+
+    n = x_pair.shape[0] // 2
+    with torch.no_grad():
+        if use_reference_modules is not None:
+            sp, mods = use_reference_modules
+            ca, cb = sp.encode(x_pair[:n]), sp.encode(x_pair[n:])
+            m = mods.matcher_new.sequential_matcher(ca["z_inv"], cb["z_inv"])["matches0"]
+            mods.pose_estimation.kabsch_transformation_estimation(ca["z_so3"] + ca["t"], (cb["z_so3"] + cb["t"])[m])
+        else:
+            ca, cb = R.encode(sd, x_pair[:n]), R.encode(sd, x_pair[n:])
+            m = R.sequential_match(ca["z_inv"], cb["z_inv"])["matches0"]
+            R.kabsch(ca["z_so3"] + ca["t"], (cb["z_so3"] + cb["t"])[m])
+
+
+def cpu_setup(sample_inst: int):
+    from oracle import p3d_shim, ref_loader
+    from oracle import restatement as R
+
+    p3d_shim.EXACT = False  # timing leg: cheapest honest fp32 kNN instead of the fp64 parity kNN
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd, wdesc = load_state_dict()
+    half = sample_inst // 2
+    ref = R.synth_instances(half, N_POINTS, 777)
+    res = R.random_rotations(half, 778) @ ref.flip(0) + 0.1
+    x = torch.cat([ref, res], 0)
+    mods, kind = None, "port"
+    if ref_loader.available() and ref_loader.checkpoint_available():
+        try:
+            mods = (ref_loader.shape_prior(sd), ref_loader.load())
+            kind = "reference"
+        except Exception:
+            mods, kind = None, "port"
+    return sd, x, mods, kind, wdesc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    sd, x, mods, kind, wdesc = cpu_setup(sample)
+    for _ in range(max(1, min(args.warmup, 1))):  # bounded: one warm-up pass is enough on the CPU
+        cpu_path_step(sd, x, mods)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_path_step(sd, x, mods)
+    dt = (time.perf_counter() - t0) / steps
+    val = sample / dt
+    cores = torch.get_num_threads()
+    sample_desc = f"{sample} instances of {N_POINTS} points per step (1 scene pair of {sample // 2}+{sample // 2}), {steps} timed steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "instances/sec (N=1024 pts) encode+match+pose", "value": val,
+        "unit": "instances/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": f"synthetic ({wdesc})",
+        "config": {"workload": "bounded CPU sample of the b200 arm's workload (256 instances x 1024 points per GPU: "
+                               "4 scene pairs x (32+32), encode + sequential match + Kabsch)", "n_points": N_POINTS},
+        "cpu_baseline": {"value": val, "unit": "instances/s", "cores": cores, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+
+    import livingscenes_b200 as ls
+    from livingscenes_b200 import _lib
+    from livingscenes_b200.dist import all_gather_codes, unpack_codes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+
+    sd, wdesc = load_state_dict()
+    model = ls.Shape_Prior.from_state_dict(sd).to(dev).eval()
+    host_sets, dev_sets = [], []
+    for k in range(N_INPUT_SETS):
+        x, _ = make_scene_batch(PAIRS_PER_GPU, 100 + 17 * k + 1000 * rank)
+        host_sets.append(x.pin_memory())
+        dev_sets.append(x.to(dev))
+    sizes = [INST_PER_SET] * PAIRS_PER_GPU
+    n_total = world * INST_PER_GPU
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step(x):
+        rec = model.encode_packed(x)["packed"]                      # [256,1028]
+        if world > 1:
+            full = all_gather_codes(rec, n_total)                    # one NCCL all-gather
+            rec = full[rank * INST_PER_GPU:(rank + 1) * INST_PER_GPU]  # this rank's scene pairs
+        code = unpack_codes(rec)
+        v = rec.view(PAIRS_PER_GPU, 2, INST_PER_SET, -1)
+        ref = unpack_codes(v[:, 0].reshape(-1, rec.shape[1]))
+        res = unpack_codes(v[:, 1].reshape(-1, rec.shape[1]))
+        m = ls.sequential_matcher_batched(ref["z_inv"].contiguous(), res["z_inv"].contiguous(), sizes, sizes)
+        # pair-local rescan index -> row in `res`
+        base = torch.arange(PAIRS_PER_GPU, device=dev).repeat_interleave(INST_PER_SET) * INST_PER_SET
+        gm = torch.where(m["matches0"] >= 0, m["matches0"] + base, m["matches0"])
+        R, t, _ = ls.kabsch_from_codes(ref, res, gm)
+        return m["matches0"], R, t, code
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(max(args.warmup, 3)):
+        step(dev_sets[w % N_INPUT_SETS])
+    barrier()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stage_ms = {}
+    launches0 = _lib.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    total_ms = 0.0
+    for k in range(args.steps):
+        flush.zero_()                                   # evict L2 between timed steps (not timed)
+        ev[k][0].record()
+        out = step(dev_sets[k % N_INPUT_SETS])
+        ev[k][1].record()
+        ev[k][1].synchronize()
+        total_ms += ev[k][0].elapsed_time(ev[k][1])
+        for name, layer, ms in _lib.profile_read():
+            stage_ms.setdefault((name, layer), []).append(ms)
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    launches = _lib.kernel_launches() - launches0
+    _lib.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- timed region 2: end to end from pinned host memory
+    h_m = torch.empty(PAIRS_PER_GPU * INST_PER_SET, dtype=torch.int64).pin_memory()
+    h_R = torch.empty(PAIRS_PER_GPU * INST_PER_SET, 3, 3).pin_memory()
+    h_t = torch.empty(PAIRS_PER_GPU * INST_PER_SET, 3, 1).pin_memory()
+    e2e_ms = 0.0
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        x = host_sets[k % N_INPUT_SETS].to(dev, non_blocking=True)
+        m0, R, t, _ = step(x)
+        h_m.copy_(m0, non_blocking=True)
+        h_R.copy_(R, non_blocking=True)
+        h_t.copy_(t, non_blocking=True)
+        b.record()
+        b.synchronize()
+        e2e_ms += a.elapsed_time(b)
+    barrier()
+    h2d = host_sets[0].numel() * 4
+    d2h = h_m.numel() * 8 + h_R.numel() * 4 + h_t.numel() * 4
+
+    # max over ranks
+    tt = torch.tensor([total_ms, e2e_ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, wall_ms = (float(v) for v in tt.tolist())
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = n_total / (ms_per_step * 1e-3)
+        e2e_val = n_total / (e2e_ms / args.steps * 1e-3)
+        # ---- roofline of the dominant fused kNN+EdgeConv launch
+        peak, peak_src, sm_max = measured_peaks()
+        geo = layer_geometry(N_POINTS)
+        knn = {l: statistics.mean(v) for (n, l), v in stage_ms.items() if n == "knn_edgeconv"}
+        dom = max(knn, key=knn.get)
+        byt, flops = knn_edge_algorithmic(geo[dom])
+        dur_s = knn[dom] * 1e-3
+        achieved = byt * INST_PER_GPU / dur_s / 1e9
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "knn_edgeconv_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(f"layer{dom}_dram_bytes_per_launch")
+        stages = {}
+        for (n, l), v in sorted(stage_ms.items()):
+            stages[f"{n}" + (f"[{l}]" if l >= 0 else "")] = round(statistics.mean(v), 4)
+        enc_ms = sum(stages.values())
+        all_layers = []
+        for l in sorted(knn):
+            b_, f_ = knn_edge_algorithmic(geo[l])
+            all_layers.append({"layer": l, "ms": round(knn[l], 4),
+                               "algorithmic_GBps": round(b_ * INST_PER_GPU / (knn[l] * 1e-3) / 1e9, 2),
+                               "reference_form_TFLOPs": round(f_ * INST_PER_GPU / (knn[l] * 1e-3) / 1e12, 2)})
+        # ---- CPU baseline (bounded sample, N=1 only)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sample = 4
+            sd_c, x_c, mods, kind, _ = cpu_setup(sample)
+            cpu_path_step(sd_c, x_c[:2], mods)  # warm-up on a smaller pair
+            t0 = time.perf_counter()
+            cpu_path_step(sd_c, x_c, mods)
+            dt = time.perf_counter() - t0
+            cpu = {"value": sample / dt, "unit": "instances/s", "cores": torch.get_num_threads(), "kind": kind,
+                   "sample": f"{sample} instances of {N_POINTS} points (1 scene pair of 2+2): encode + sequential "
+                             f"match + Kabsch, 1 timed pass after 1 warm-up ({dt:.1f} s)"}
+        line = {
+            "metric": "instances/sec (N=1024 pts) encode+match+pose", "value": value, "unit": "instances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": f"synthetic ({wdesc})",
+            "config": {"workload": "BASELINE config[1]: 256 synthetic instances x 1024 points per GPU = 4 scene pairs x "
+                                   "(32 ref + 32 rescan); Shape_Prior.encode + sequential_matcher + Kabsch per matched pair",
+                       "instances_per_gpu": INST_PER_GPU, "n_points": N_POINTS, "pairs_per_gpu": PAIRS_PER_GPU,
+                       "parallelism": f"instance-sharded x{world}" + (" + 1 NCCL all-gather of packed codes" if world > 1 else ""),
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set ~2 GB >> 126 MB L2",
+                       "timing": "CUDA events per step on the launching stream, summed over K steps, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": f"k_knn_edge (fused kNN+EdgeConv+pool) layer {dom}",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "launch_ms": knn[dom], "algorithmic_bytes_per_launch": byt * INST_PER_GPU,
+                         "share_of_encoder": knn[dom] / enc_ms,
+                         "note": "this kernel is FP32-ALU / L2-gather bound, not HBM bound (SURVEY.md 8d); see fp32",
+                         "fp32": {"achieved_TFLOPs_reference_form": flops * INST_PER_GPU / dur_s / 1e12,
+                                  "peak_TFLOPs_derived": fp32_peak, "frac": flops * INST_PER_GPU / dur_s / 1e12 / fp32_peak},
+                         "all_layers": all_layers},
+            "cpu_baseline": cpu,
+            "stages_ms": stages,
+            "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,9 @@ class DecoderDesc(C.Structure):
 _PROTOS = {
     "ls_version": (C.c_int, []),
     "ls_last_error": (C.c_char_p, []),
+    "ls_profile_enable": (C.c_int, [C.c_int32]),
+    "ls_profile_read": (C.c_int, [c_i32_p, c_i32_p, c_float_p, C.c_int32, c_i32_p]),
+    "ls_kernel_launches": (C.c_int64, []),
     "ls_encoder_workspace_bytes": (C.c_int, [C.POINTER(EncoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "ls_encoder_forward": (C.c_int, [C.POINTER(EncoderDesc), C.POINTER(EncoderIO), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -130,3 +133,22 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(
             f"livingscenes_b200: `{name}` must be a CUDA tensor; this package has no CPU path "
             "(the CPU restatement lives in oracle/ and is test infrastructure only).")
+
+
+STAGE_NAMES = ("normalize", "fps", "gather", "gemm_tables", "knn_edgeconv", "global_conv", "head")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().ls_profile_enable(int(on)), "ls_profile_enable")
+
+
+def profile_read():
+    """[(stage_name, layer, ms)] of the last encoder forward (synchronise the stream first)."""
+    n = 64
+    st, ly, ms, cnt = (C.c_int32 * n)(), (C.c_int32 * n)(), (C.c_float * n)(), C.c_int32(0)
+    check(lib().ls_profile_read(st, ly, ms, n, C.byref(cnt)), "ls_profile_read")
+    return [(STAGE_NAMES[st[i]], int(ly[i]), float(ms[i])) for i in range(cnt.value)]
+
+
+def kernel_launches() -> int:
+    return int(lib().ls_kernel_launches())

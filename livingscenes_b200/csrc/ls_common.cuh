@@ -10,6 +10,7 @@
 namespace ls {
 
 void set_error(const std::string& msg);
+void count_launch();
 
 #define LS_CHECK_CUDA(expr)                                                                 \
     do {                                                                                    \
@@ -27,6 +28,7 @@ void set_error(const std::string& msg);
             ls::set_error(std::string("launch of ") + name + ": " + cudaGetErrorString(_e)); \
             return LS_ERR_CUDA;                                                             \
         }                                                                                   \
+        ls::count_launch();                                                                 \
     } while (0)
 
 #define LS_REQUIRE(cond, msg)                                                               \

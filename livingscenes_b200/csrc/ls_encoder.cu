@@ -2,6 +2,8 @@
 //   ls_encoder_forward   VecDGCNN_att.forward / Shape_Prior.encode
 //   ls_knn, ls_fps       the pytorch3d boundary as stand-alone ops
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <vector>
 
 #include "ls_encoder_kernels.cuh"
@@ -10,6 +12,38 @@ namespace ls {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-stage CUDA-event timing of the last ls_encoder_forward call
+struct ProfEntry {
+    cudaEvent_t a, b;
+    int stage, layer;
+};
+static std::vector<ProfEntry> g_prof;
+static int g_prof_n = 0;
+static bool g_prof_on = false;
+
+struct ProfScope {
+    cudaStream_t st;
+    int slot = -1;
+    ProfScope(int stage, int layer, cudaStream_t s) : st(s) {
+        if (!g_prof_on) return;
+        if (g_prof_n == (int)g_prof.size()) {
+            ProfEntry e{};
+            if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+            g_prof.push_back(e);
+        }
+        slot = g_prof_n++;
+        g_prof[slot].stage = stage;
+        g_prof[slot].layer = layer;
+        cudaEventRecord(g_prof[slot].a, st);
+    }
+    ~ProfScope() {
+        if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+    }
+};
 
 namespace {
 
@@ -160,6 +194,23 @@ using namespace ls;
 extern "C" {
 
 int ls_version(void) { return LS_ABI_VERSION; }
+int64_t ls_kernel_launches(void) { return (int64_t)ls::g_launches.load(); }
+int ls_profile_enable(int32_t on) {
+    ls::g_prof_on = on != 0;
+    ls::g_prof_n = 0;
+    return LS_OK;
+}
+int ls_profile_read(int32_t* stage, int32_t* layer, float* ms, int32_t max_entries, int32_t* n_entries) {
+    LS_REQUIRE(stage && layer && ms && n_entries, "null pointer");
+    int n = ls::g_prof_n < max_entries ? ls::g_prof_n : max_entries;
+    for (int i = 0; i < n; ++i) {
+        stage[i] = ls::g_prof[i].stage;
+        layer[i] = ls::g_prof[i].layer;
+        LS_CHECK_CUDA(cudaEventElapsedTime(&ms[i], ls::g_prof[i].a, ls::g_prof[i].b));
+    }
+    *n_entries = n;
+    return LS_OK;
+}
 const char* ls_last_error(void) { return ls::g_last_error.c_str(); }
 
 int ls_encoder_workspace_bytes(const ls_encoder_desc* desc, int32_t B, int32_t N, size_t* bytes) {
@@ -190,10 +241,12 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float oms = 1.f - d->neg_slope;
+    g_prof_n = 0;
 
     // ---- pre-processing (Shape_Prior.encode) ------------------------------------------------
     const float* x = io->x;
     if (io->normalize) {
+        ProfScope ps(0, -1, st);
         const size_t smem = (size_t)(3 * N + 64) * sizeof(float);
         LS_REQUIRE(smem <= 200 * 1024, "normalize: N too large for the shared-memory resident cloud");
         LS_CHECK_CUDA(cudaFuncSetAttribute(k_normalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -222,6 +275,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             }
         }
         if (fa.n_levels > 0) {
+            ProfScope ps(1, -1, st);
             rc = launch_fps(fa, B, st);
             if (rc != LS_OK) return rc;
         }
@@ -236,6 +290,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         const int Ns = p.n_src[i], Nd = p.n_dst[i], Ci = L.c_in, Co = L.c_out;
         const float* dst_f = src_f;
         if (L.down_factor > 1) {
+            ProfScope ps(2, i, st);
             dim3 g((Nd + 127) / 128, Ci * 3, B);
             k_gather_points<<<g, 128, 0, st>>>(src_f, p.sel[i], Ci * 3, Ns, Nd, p.dstf);
             LS_CHECK_LAUNCH("k_gather_points");
@@ -258,11 +313,13 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         ea.idx_in = io->force_knn_idx[i];
         if (i == 0) {
             ea.w0 = L.w0;
+            ProfScope ps(4, i, st);
             rc = launch_edge(MODE_L0, ea, st);
             if (rc != LS_OK) return rc;
         } else {
             const int nb = L.attention ? 2 : 1;
             const int r_src = 2 * nb * Co, r_dst = (2 * nb + (L.attention ? 2 : 0)) * Co;
+            std::unique_ptr<ProfScope> pg(new ProfScope(3, i, st));
             GemmArgs g{};
             g.K = Ci;
             g.ldw = Ci;
@@ -290,7 +347,9 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             g.x_sk = 3LL * Nd;
             g.out = p.pdst;
             rc = launch_gemm(g, st);
+            pg.reset();
             if (rc != LS_OK) return rc;
+            ProfScope ps(4, i, st);
             ea.psrc = p.psrc;
             ea.pdst = p.pdst;
             ea.row_s = r_src * 3;
@@ -299,6 +358,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             if (rc != LS_OK) return rc;
         }
         if (L.global_conv) {
+            ProfScope ps(5, i, st);
             k_mean_bias<<<B, 256, (size_t)Co * 3 * sizeof(float), st>>>(p.pooled, Co, Nd, L.w_g2, p.bias);
             LS_CHECK_LAUNCH("k_mean_bias");
             GemmArgs g{};
@@ -334,6 +394,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
 
     // ---- head ------------------------------------------------------------------------------
     {
+        ProfScope ps(6, -1, st);
         const int last = d->num_layers - 1;
         const int Cl = d->layers[last].c_out, Nl = p.n_dst[last], C = d->c_dim;
         GemmArgs g{};

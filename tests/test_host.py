@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     from livingscenes_b200 import _lib
 
     header = open(os.path.join(ROOT, "include", "livingscenes_b200.h")).read()
-    declared = set(re.findall(r"LS_API\s+(?:const\s+char\*|int)\s+(ls_\w+)\s*\(", header))
+    declared = set(re.findall(r"LS_API\s+(?:const\s+char\*|int64_t|int)\s+(ls_\w+)\s*\(", header))
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     handle = _lib.lib()
     for name in declared:
