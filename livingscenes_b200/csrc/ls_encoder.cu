@@ -60,9 +60,12 @@ struct Carver {
     }
 };
 
+constexpr int SMALL_NS = 128;  // source sets up to this size take the k_knn_small path
+
 struct Plan {
     int n_src[LS_MAX_LAYERS], n_dst[LS_MAX_LAYERS];
     float *xn, *centroid, *s0, *featA, *featB, *dstf, *pooled, *raw, *psrc, *pdst, *bias;
+    int64_t* small_idx;
     int* sel[LS_MAX_LAYERS];
     size_t bytes;
 };
@@ -98,7 +101,7 @@ int check_desc(const ls_encoder_desc* d, int N) {
 
 void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
     Carver c(ws);
-    size_t feat = 0, dstf = 0, pooled = 0, raw = 0, psrc = 0, pdst = 0, bias = 0;
+    size_t feat = 0, dstf = 0, pooled = 0, raw = 0, psrc = 0, pdst = 0, bias = 0, small = 0;
     int n = N;
     for (int i = 0; i < d->num_layers; ++i) {
         const ls_enc_layer_desc& L = d->layers[i];
@@ -106,6 +109,7 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
         n /= L.down_factor;
         p.n_dst[i] = n;
         const size_t co = L.c_out, ci = L.c_in;
+        if (p.n_src[i] <= SMALL_NS) small = std::max(small, (size_t)n * LS_KNN_K);
         feat = std::max(feat, co * 3 * (size_t)n);
         if (L.down_factor > 1) dstf = std::max(dstf, ci * 3 * (size_t)n);
         if (L.global_conv) {
@@ -131,6 +135,7 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
     p.psrc = c.take<float>((size_t)B * std::max<size_t>(psrc, 1));
     p.pdst = c.take<float>((size_t)B * std::max<size_t>(pdst, 1));
     p.bias = c.take<float>((size_t)B * std::max<size_t>(bias, 1));
+    p.small_idx = c.take<int64_t>((size_t)B * std::max<size_t>(small, 1));
     for (int i = 0; i < d->num_layers; ++i)
         p.sel[i] = d->layers[i].down_factor > 1 ? c.take<int>((size_t)B * p.n_dst[i]) : nullptr;
     p.bytes = (c.off + 255) & ~size_t(255);
@@ -150,8 +155,17 @@ int launch_edge_cpl(const EdgeArgs& a, int cpl, dim3 grid, cudaStream_t st) {
     return LS_OK;
 }
 
+// dst points per CTA: as many as the tile holds, fewer when the grid would not fill the GPU twice
+int pick_qpc(int B, int Nd, bool phase2_only) {
+    int qpc = QT;
+    const int floor_q = phase2_only ? 8 : 16;
+    while (qpc > floor_q && (long long)B * ((Nd + qpc - 1) / qpc) < 4 * 148) qpc >>= 1;
+    return qpc;
+}
+
 int launch_edge(int mode, const EdgeArgs& a, cudaStream_t st) {
-    dim3 grid((a.Nd + QT - 1) / QT, a.B);
+    LS_REQUIRE(a.qpc >= 8 && a.qpc <= QT && a.qpc % 8 == 0, "bad qpc");
+    dim3 grid((a.Nd + a.qpc - 1) / a.qpc, a.B);
     const int cpl = a.Co / 32;
     if (mode == MODE_L0) return launch_edge_cpl<MODE_L0>(a, cpl, grid, st);
     if (mode == MODE_MEAN) return launch_edge_cpl<MODE_MEAN>(a, cpl, grid, st);
@@ -311,6 +325,14 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         ea.out = edge_out;
         ea.idx_out = io->knn_idx[i];
         ea.idx_in = io->force_knn_idx[i];
+        if (ea.idx_in == nullptr && Ns <= SMALL_NS) {
+            ProfScope ps(4, i, st);
+            dim3 gs((Nd + 7) / 8, B);
+            k_knn_small<<<gs, 256, 0, st>>>(src_f, dst_f, Ci * 3, Ns, Nd, p.small_idx, nullptr);
+            LS_CHECK_LAUNCH("k_knn_small");
+            ea.idx_in = p.small_idx;
+        }
+        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr);
         if (i == 0) {
             ea.w0 = L.w0;
             ProfScope ps(4, i, st);
@@ -455,6 +477,13 @@ int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_
     ea.Co = 32;
     ea.idx_out = idx;
     ea.dist_out = dist2;
+    if (Ns <= SMALL_NS) {
+        dim3 gs((Nq + 7) / 8, B);
+        k_knn_small<<<gs, 256, 0, static_cast<cudaStream_t>(stream)>>>(source, query, D, Ns, Nq, idx, dist2);
+        LS_CHECK_LAUNCH("k_knn_small");
+        return LS_OK;
+    }
+    ea.qpc = pick_qpc(B, Nq, false);
     return launch_edge(MODE_KNN_ONLY, ea, static_cast<cudaStream_t>(stream));
 }
 

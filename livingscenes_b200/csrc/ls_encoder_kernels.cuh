@@ -281,13 +281,14 @@ __global__ void k_gather_points(const float* __restrict__ in, const int* __restr
 //              MODE_L0   : layer 0 builds its 3-channel edge feature [cross, nn-dst, dst]
 //                          directly from xyz (vec_dgcnn_atten.py:153-158).
 // ============================================================================================
-constexpr int QT = 64, ST = 256, DKC = 8, EDGE_THREADS = 256;
+constexpr int QT = 64, ST = 256, DKC = 8, EDGE_THREADS = 256, QCAP = 32;
 enum { MODE_L0 = 0, MODE_MEAN = 1, MODE_ATT = 2, MODE_KNN_ONLY = 3 };
 
 struct EdgeArgs {
     const float* src_f;  // [B][D][Ns] kNN features of the sources (xyz for layer 0)
     const float* dst_f;  // [B][D][Nd] kNN features of the queries
     int B, D, Ns, Nd;
+    int qpc;             // dst points handled per CTA (multiple of 8, <= QT)
     const float* psrc;   // [B][Ns][row_s]  gather table  (parts Vq,Vk[,Kq,Kk] x 3 axes x Co)
     const float* pdst;   // [B][Nd][row_d]  dst table     (parts Vq,Vk[,Kq,Kk,Qq,Qk])
     int row_s, row_d;
@@ -295,24 +296,67 @@ struct EdgeArgs {
     int Co;
     float oms;           // 1 - negative slope
     float* out;          // [B][Co][3][Nd]
-    int64_t* idx_out;         // optional [B][Nd][16]
-    const int64_t* idx_in;   // optional forced graph
-    float* dist_out;           // optional [B][Nd][16] (MODE_KNN_ONLY)
+    int64_t* idx_out;        // optional [B][Nd][16]
+    const int64_t* idx_in;   // optional: graph given (teacher forcing, or built by k_knn_small)
+    float* dist_out;         // optional [B][Nd][16] (MODE_KNN_ONLY)
 };
 
-__device__ __forceinline__ void topk_insert(float& ld, int& li, float cd, int ci, int lane) {
-    const bool worse = (ld > cd) || (ld == cd && li > ci);
-    const unsigned m = __ballot_sync(FULL, worse);
-    const float dn = __shfl_up_sync(FULL, ld, 1);
-    const int in = __shfl_up_sync(FULL, li, 1);
-    const int pos = __ffs(m) - 1;
-    if (lane == pos) {
-        ld = cd;
-        li = ci;
-    } else if (lane > pos) {
-        ld = dn;
-        li = in;
+// ---- warp-level top-k machinery: one (distance, index) element per lane, lexicographic order so
+//      that ties resolve towards the LOWER source index, as pytorch3d's strict '<' replacement does.
+__device__ __forceinline__ bool lex_less(float d1, int i1, float d2, int i2) {
+    return d1 < d2 || (d1 == d2 && i1 < i2);
+}
+__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane, bool desc) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float od = __shfl_xor_sync(FULL, d, j);
+            const int oi = __shfl_xor_sync(FULL, i, j);
+            const bool up = (((lane & k) == 0) != desc);
+            const bool lower = (lane & j) == 0;
+            const bool take = (lower == up) ? lex_less(od, oi, d, i) : lex_less(d, i, od, oi);
+            if (take) {
+                d = od;
+                i = oi;
+            }
+        }
     }
+}
+__device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const float od = __shfl_xor_sync(FULL, d, j);
+        const int oi = __shfl_xor_sync(FULL, i, j);
+        const bool take = ((lane & j) == 0) ? lex_less(od, oi, d, i) : lex_less(d, i, od, oi);
+        if (take) {
+            d = od;
+            i = oi;
+        }
+    }
+}
+// A: ascending over the 32 lanes.  B: arbitrary.  Result: the 32 smallest of A u B, ascending, in A.
+__device__ __forceinline__ void merge_keep32(float& ad, int& ai, float bd, int bi, int lane) {
+    bitonic_sort32(bd, bi, lane, /*desc=*/true);
+    if (lex_less(bd, bi, ad, ai)) {  // half-cleaner of the bitonic sequence A ++ B
+        ad = bd;
+        ai = bi;
+    }
+    bitonic_merge32(ad, ai, lane);
+}
+// 16th smallest of 32 lane values (value-only bitonic sort)
+__device__ __forceinline__ float warp_kth16(float v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const float o = __shfl_xor_sync(FULL, v, j);
+            const bool up = (lane & k) == 0;
+            const bool lower = (lane & j) == 0;
+            v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+        }
+    }
+    return __shfl_sync(FULL, v, 15);
 }
 
 template <int MODE, int CPL>
@@ -324,16 +368,20 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     __shared__ __align__(16) float sbuf[BUF_FLOATS];
     __shared__ int sIdx[QT][LS_KNN_K];
     __shared__ float sDist[(MODE == MODE_KNN_ONLY) ? QT : 1][LS_KNN_K];
+    __shared__ float sQd[8][8][QCAP];  // [warp][query][slot] candidate queues
+    __shared__ int sQi[8][8][QCAP];
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int b = blockIdx.y;
-    const int q0 = blockIdx.x * QT;
+    const int qpc = a.qpc;
+    const int q0 = blockIdx.x * qpc;
     const int Ns = a.Ns, Nd = a.Nd, D = a.D;
+    const int nq = min(qpc, Nd - q0);  // valid dst points of this CTA
 
     if (a.idx_in != nullptr) {
-        for (int e = t; e < QT * LS_KNN_K; e += EDGE_THREADS) {
-            int ql = e >> 4, k = e & 15, n = q0 + ql;
-            sIdx[ql][k] = n < Nd ? (int)a.idx_in[((size_t)b * Nd + n) * LS_KNN_K + k] : 0;
+        for (int e = t; e < nq * LS_KNN_K; e += EDGE_THREADS) {
+            int ql = e >> 4, k = e & 15;
+            sIdx[ql][k] = (int)a.idx_in[((size_t)b * Nd + q0 + ql) * LS_KNN_K + k];
         }
     } else {
         // ------------------------------------------------------------------ phase 1: kNN
@@ -344,6 +392,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
         const int n_tiles = (Ns + ST - 1) / ST;
         const int n_chunks = (D + DKC - 1) / DKC;
         const int n_it = n_tiles * n_chunks;
+        const bool warp_on = w * 8 < nq;  // warps without valid queries only help staging the tiles
 
         float sreg[DKC], qreg[2];
         auto g_load = [&](int it) {
@@ -354,11 +403,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
                 int d = d0 + dd;
                 sreg[dd] = (s < Ns && d < D) ? __ldg(srcb + (size_t)d * Ns + s) : 0.f;
             }
-            const int q = q0 + (t & 63);
+            const int ql = t & 63;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 int d = d0 + (t >> 6) + 4 * i;
-                qreg[i] = (q < Nd && d < D) ? __ldg(dstb + (size_t)d * Nd + q) : 0.f;
+                qreg[i] = (ql < nq && d < D) ? __ldg(dstb + (size_t)d * Nd + q0 + ql) : 0.f;
             }
         };
         auto s_store = [&](int buf) {
@@ -368,12 +417,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
             for (int i = 0; i < 2; ++i) Qs[buf][(t >> 6) + 4 * i][t & 63] = qreg[i];
         };
 
+        // per query: the 32 best so far, ascending over the lanes (entry 15 is the running 16th)
         float ld[8], acc[8][8];
-        int li[8];
+        int li[8], cnt[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             ld[i] = FLT_MAX;
-            li[i] = 0;
+            li[i] = 0x7fffffff;
+            cnt[i] = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
         }
@@ -384,48 +435,78 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
         for (int it = 0; it < n_it; ++it) {
             const int buf = it & 1;
             if (it + 1 < n_it) g_load(it + 1);
+            if (warp_on) {
 #pragma unroll
-            for (int dd = 0; dd < DKC; ++dd) {
-                const float4 qa = *reinterpret_cast<const float4*>(&Qs[buf][dd][w * 8]);
-                const float4 qb = *reinterpret_cast<const float4*>(&Qs[buf][dd][w * 8 + 4]);
-                const float4 sa = *reinterpret_cast<const float4*>(&Ss[buf][dd][lane * 4]);
-                const float4 sb = *reinterpret_cast<const float4*>(&Ss[buf][dd][128 + lane * 4]);
-                const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                for (int dd = 0; dd < DKC; ++dd) {
+                    const float4 qa = *reinterpret_cast<const float4*>(&Qs[buf][dd][w * 8]);
+                    const float4 qb = *reinterpret_cast<const float4*>(&Qs[buf][dd][w * 8 + 4]);
+                    const float4 sa = *reinterpret_cast<const float4*>(&Ss[buf][dd][lane * 4]);
+                    const float4 sb = *reinterpret_cast<const float4*>(&Ss[buf][dd][128 + lane * 4]);
+                    const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+                    const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float df = qv[i] - sv[j];
-                        acc[i][j] = fmaf(df, df, acc[i][j]);
-                    }
-            }
-            const int tile = it / n_chunks, chunk = it - tile * n_chunks;
-            if (chunk == n_chunks - 1) {
-                // ---- merge this tile's 8 x (32 x 8) candidates into the running top-16 lists
-                const int sbase = tile * ST + lane * 4;
-#pragma unroll
-                for (int qi = 0; qi < 8; ++qi) {
-                    float tau = __shfl_sync(FULL, ld[qi], 15);
-                    int taui = __shfl_sync(FULL, li[qi], 15);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float d = acc[qi][j];
-                        const int s = sbase + (j < 4 ? j : 124 + j);
-                        const bool ok = (s < Ns) && (d < tau || (d == tau && s < taui));
-                        unsigned m = __ballot_sync(FULL, ok);
-                        while (m) {
-                            const int src = __ffs(m) - 1;
-                            m &= m - 1;
-                            const float cd = __shfl_sync(FULL, d, src);
-                            const int ci = __shfl_sync(FULL, s, src);
-                            if (cd < tau || (cd == tau && ci < taui)) {
-                                topk_insert(ld[qi], li[qi], cd, ci, lane);
-                                tau = __shfl_sync(FULL, ld[qi], 15);
-                                taui = __shfl_sync(FULL, li[qi], 15);
-                            }
+                        for (int j = 0; j < 8; ++j) {
+                            const float df = qv[i] - sv[j];
+                            acc[i][j] = fmaf(df, df, acc[i][j]);
                         }
-                        acc[qi][j] = 0.f;
+                }
+                const int tile = it / n_chunks, chunk = it - tile * n_chunks;
+                if (chunk == n_chunks - 1) {
+                    // ---- this tile's 8 x (32 lanes x 8) distances are final: keep what can still be
+                    //      among the 16 nearest.  Candidates below the running threshold are compacted
+                    //      (ballot + popc) into a per-query shared-memory queue; a full queue is merged
+                    //      into the sorted list with a warp bitonic network.
+                    const int sbase = tile * ST + lane * 4;
+                    const bool last_tile = tile == n_tiles - 1;
+#pragma unroll
+                    for (int qi = 0; qi < 8; ++qi) {
+                        float tau = __shfl_sync(FULL, ld[qi], 15);
+                        int taui = __shfl_sync(FULL, li[qi], 15);
+                        if (tile == 0) {
+                            // 16th smallest of the 32 lane minima bounds the 16th smallest candidate
+                            float mn = FLT_MAX;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                mn = (sbase + (j < 4 ? j : 124 + j) < Ns) ? fminf(mn, acc[qi][j]) : mn;
+                            tau = warp_kth16(mn, lane);
+                            taui = 0x7fffffff;
+                        }
+                        float* qd = sQd[w][qi];
+                        int* qx = sQi[w][qi];
+                        auto flush = [&]() {
+                            __syncwarp();
+                            const float bd = lane < cnt[qi] ? qd[lane] : FLT_MAX;
+                            const int bi = lane < cnt[qi] ? qx[lane] : 0x7fffffff;
+                            __syncwarp();
+                            merge_keep32(ld[qi], li[qi], bd, bi, lane);
+                            cnt[qi] = 0;
+                            tau = __shfl_sync(FULL, ld[qi], 15);
+                            taui = __shfl_sync(FULL, li[qi], 15);
+                        };
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float d = acc[qi][j];
+                            const int s = sbase + (j < 4 ? j : 124 + j);
+                            bool ok = (s < Ns) && lex_less(d, s, tau, taui);
+                            unsigned m = __ballot_sync(FULL, ok);
+                            if (m) {
+                                if (cnt[qi] + __popc(m) > QCAP) {
+                                    flush();
+                                    ok = ok && lex_less(d, s, tau, taui);
+                                    m = __ballot_sync(FULL, ok);
+                                }
+                                if (ok) {
+                                    const int pos = cnt[qi] + __popc(m & ((1u << lane) - 1u));
+                                    qd[pos] = d;
+                                    qx[pos] = s;
+                                }
+                                cnt[qi] += __popc(m);
+                            }
+                            acc[qi][j] = 0.f;
+                        }
+                        if (cnt[qi] > 16 || (last_tile && cnt[qi] > 0)) flush();
                     }
                 }
             }
@@ -434,10 +515,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
                 __syncthreads();
             }
         }
-        if (lane < LS_KNN_K) {
+        if (warp_on && lane < LS_KNN_K) {
 #pragma unroll
             for (int qi = 0; qi < 8; ++qi) {
-                sIdx[w * 8 + qi][lane] = li[qi];
+                sIdx[w * 8 + qi][lane] = min(li[qi], Ns - 1);  // NaN features: stay in bounds
                 if (MODE == MODE_KNN_ONLY) sDist[w * 8 + qi][lane] = ld[qi];
             }
         }
@@ -445,16 +526,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     __syncthreads();
 
     if (a.idx_out != nullptr) {
-        for (int e = t; e < QT * LS_KNN_K; e += EDGE_THREADS) {
-            int ql = e >> 4, k = e & 15, n = q0 + ql;
-            if (n < Nd) a.idx_out[((size_t)b * Nd + n) * LS_KNN_K + k] = sIdx[ql][k];
+        for (int e = t; e < nq * LS_KNN_K; e += EDGE_THREADS) {
+            int ql = e >> 4, k = e & 15;
+            a.idx_out[((size_t)b * Nd + q0 + ql) * LS_KNN_K + k] = sIdx[ql][k];
         }
     }
     if (MODE == MODE_KNN_ONLY) {
         if (a.dist_out != nullptr) {
-            for (int e = t; e < QT * LS_KNN_K; e += EDGE_THREADS) {
-                int ql = e >> 4, k = e & 15, n = q0 + ql;
-                if (n < Nd) a.dist_out[((size_t)b * Nd + n) * LS_KNN_K + k] = sDist[ql][k];
+            for (int e = t; e < nq * LS_KNN_K; e += EDGE_THREADS) {
+                int ql = e >> 4, k = e & 15;
+                a.dist_out[((size_t)b * Nd + q0 + ql) * LS_KNN_K + k] = sDist[ql][k];
             }
         }
         return;
@@ -467,9 +548,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
 
     if (MODE == MODE_L0) {
         const float* xyz = a.src_f + (size_t)b * 3 * Ns;  // layer 0: Ns == Nd, src == dst
-        for (int qi = 0; qi < 8; ++qi) {
-            const int ql = w * 8 + qi, n = q0 + ql;
-            if (n >= Nd) break;
+        for (int ql = w; ql < nq; ql += 8) {
+            const int n = q0 + ql;
             const float x0 = __ldg(xyz + n), x1 = __ldg(xyz + Ns + n), x2 = __ldg(xyz + 2 * Ns + n);
             const float nr = fmaxf(sqrtf(fmaf(x2, x2, fmaf(x1, x1, x0 * x0))), EPS_NRM);
             const float h0 = x0 / nr, h1 = x1 / nr, h2 = x2 / nr;
@@ -513,9 +593,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     const int C3 = 3 * Co;  // floats per part
 
     if (MODE == MODE_MEAN) {
-        for (int qi = 0; qi < 8; ++qi) {
-            const int ql = w * 8 + qi, n = q0 + ql;
-            if (n >= Nd) break;
+        for (int ql = w; ql < nq; ql += 8) {
+            const int n = q0 + ql;
             const float* Pd = a.pdst + ((size_t)b * Nd + n) * a.row_d;
 #pragma unroll 1
             for (int j = 0; j < CPL; ++j) {
@@ -547,9 +626,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     if (MODE == MODE_ATT) {
         float* sR = sbuf + (size_t)w * CPL * 32;  // [CPL][32] per warp (phase-1 tiles are dead)
         const float inv_sqrt = rsqrtf(3.f * (float)LS_HEAD_C);
-        for (int qi = 0; qi < 8; ++qi) {
-            const int ql = w * 8 + qi, n = q0 + ql;
-            if (n >= Nd) break;
+        for (int ql = w; ql < nq; ql += 8) {
+            const int n = q0 + ql;
             const float* Pd = a.pdst + ((size_t)b * Nd + n) * a.row_d;
             // ---- |Q|: channel-norm of the activated query feature (cevn, vec_layers.py:24-31)
             float ssum = 0.f;
@@ -643,6 +721,48 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
             }
             __syncwarp();
         }
+    }
+}
+
+// ============================================================================================
+// kNN for small source sets (Ns <= 128: the deep, heavily down-sampled layers).  One warp per query,
+// lanes over sources (<= 4 per lane), features streamed from L1/L2, top-16 by warp bitonic merges.
+// Writes the graph that the phase-2-only launch of k_knn_edge then consumes (idx_in).
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_knn_small(const float* __restrict__ src_f, const float* __restrict__ dst_f,
+                                                   int D, int Ns, int Nd, int64_t* __restrict__ idx_out,
+                                                   float* __restrict__ dist_out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y, n = blockIdx.x * 8 + w;
+    if (n >= Nd) return;
+    const float* srcb = src_f + (size_t)b * D * Ns;
+    const float* dstb = dst_f + (size_t)b * D * Nd + n;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+        const float q = __ldg(dstb + (size_t)d * Nd);
+        const float* sr = srcb + (size_t)d * Ns + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (lane + 32 * j < Ns) {
+                const float df = q - __ldg(sr + 32 * j);
+                acc[j] = fmaf(df, df, acc[j]);
+            }
+        }
+    }
+    float ad = lane < Ns ? acc[0] : FLT_MAX;
+    int ai = lane < Ns ? lane : 0x7fffffff;
+    bitonic_sort32(ad, ai, lane, false);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+        if (32 * j < Ns) {  // warp-uniform
+            const int s = lane + 32 * j;
+            merge_keep32(ad, ai, s < Ns ? acc[j] : FLT_MAX, s < Ns ? s : 0x7fffffff, lane);
+        }
+    }
+    if (lane < LS_KNN_K) {
+        idx_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = min(ai, Ns - 1);
+        if (dist_out) dist_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = ad;
     }
 }
 
