@@ -301,48 +301,36 @@ struct EdgeArgs {
     float* dist_out;         // optional [B][Nd][16] (MODE_KNN_ONLY)
 };
 
-// ---- warp-level top-k machinery: one (distance, index) element per lane, lexicographic order so
-//      that ties resolve towards the LOWER source index, as pytorch3d's strict '<' replacement does.
-__device__ __forceinline__ bool lex_less(float d1, int i1, float d2, int i2) {
-    return d1 < d2 || (d1 == d2 && i1 < i2);
+// ---- warp-level top-k machinery.  A candidate is ONE 64-bit key: (float bits of the squared distance
+//      << 32) | source index.  Squared distances are >= +0, so unsigned integer order on the key is
+//      exactly the lexicographic (distance, index) order: ties resolve towards the LOWER source index,
+//      as pytorch3d's strict '<' replacement does, and a NaN distance sorts after everything.
+typedef unsigned long long u64;
+constexpr u64 KEY_MAX = ~0ull;
+__device__ __forceinline__ u64 make_key(float d, int s) {
+    return ((u64)__float_as_uint(d) << 32) | (unsigned)s;
 }
-__device__ __forceinline__ void bitonic_sort32(float& d, int& i, int lane, bool desc) {
+__device__ __forceinline__ float key_dist(u64 k) { return __uint_as_float((unsigned)(k >> 32)); }
+__device__ __forceinline__ int key_idx(u64 k) { return (int)(unsigned)(k & 0xffffffffu); }
+
+__device__ __forceinline__ void bitonic_sort32(u64& v, int lane, bool desc) {
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const float od = __shfl_xor_sync(FULL, d, j);
-            const int oi = __shfl_xor_sync(FULL, i, j);
+            const u64 o = __shfl_xor_sync(FULL, v, j);
             const bool up = (((lane & k) == 0) != desc);
             const bool lower = (lane & j) == 0;
-            const bool take = (lower == up) ? lex_less(od, oi, d, i) : lex_less(d, i, od, oi);
-            if (take) {
-                d = od;
-                i = oi;
-            }
+            v = (lower == up) ? (o < v ? o : v) : (o > v ? o : v);
         }
     }
 }
-__device__ __forceinline__ void bitonic_merge32(float& d, int& i, int lane) {
+__device__ __forceinline__ void bitonic_merge32(u64& v, int lane) {
 #pragma unroll
     for (int j = 16; j > 0; j >>= 1) {
-        const float od = __shfl_xor_sync(FULL, d, j);
-        const int oi = __shfl_xor_sync(FULL, i, j);
-        const bool take = ((lane & j) == 0) ? lex_less(od, oi, d, i) : lex_less(d, i, od, oi);
-        if (take) {
-            d = od;
-            i = oi;
-        }
+        const u64 o = __shfl_xor_sync(FULL, v, j);
+        v = ((lane & j) == 0) ? (o < v ? o : v) : (o > v ? o : v);
     }
-}
-// A: ascending over the 32 lanes.  B: arbitrary.  Result: the 32 smallest of A u B, ascending, in A.
-__device__ __forceinline__ void merge_keep32(float& ad, int& ai, float bd, int bi, int lane) {
-    bitonic_sort32(bd, bi, lane, /*desc=*/true);
-    if (lex_less(bd, bi, ad, ai)) {  // half-cleaner of the bitonic sequence A ++ B
-        ad = bd;
-        ai = bi;
-    }
-    bitonic_merge32(ad, ai, lane);
 }
 // 16th smallest of 32 lane values (value-only bitonic sort)
 __device__ __forceinline__ float warp_kth16(float v, int lane) {
@@ -358,6 +346,62 @@ __device__ __forceinline__ float warp_kth16(float v, int lane) {
     }
     return __shfl_sync(FULL, v, 15);
 }
+// Out-of-line on purpose: the fused kernel calls these from unrolled per-query sites; inlining the
+// sorting networks there blows the kernel up to >1 MB of SASS and thrashes the instruction cache.
+__device__ __noinline__ float warp_kth16_nl(float v) { return warp_kth16(v, threadIdx.x & 31); }
+
+// Merge a query's shared-memory queue (cnt <= 32 unsorted keys) into its sorted list (one key per lane,
+// ascending; only entries 0..15 are ever consumed).  Returns the new list element of this lane.
+__device__ __noinline__ u64 knn_flush(u64 lk, const u64* q, int cnt) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    const bool empty = __shfl_sync(FULL, lk, 0) == KEY_MAX;
+    if (empty || cnt <= 16) {
+        // the 16 kept list entries and up to 16 (32 if the list is empty) queue entries fit one 32-sort
+        const int qi = empty ? lane : lane - 16;
+        u64 v = (!empty && lane < 16) ? lk : ((qi >= 0 && qi < cnt) ? q[qi] : KEY_MAX);
+        bitonic_sort32(v, lane, false);
+        return v;
+    }
+    u64 b = lane < cnt ? q[lane] : KEY_MAX;
+    bitonic_sort32(b, lane, true);
+    lk = b < lk ? b : lk;  // half-cleaner of the bitonic sequence (ascending list) ++ (descending queue)
+    bitonic_merge32(lk, lane);
+    return lk;
+}
+
+// Slow path of the per-tile selection (queue overflow): slot by slot, each slot holds at most 32
+// candidates so it always fits after a flush.  keys[j] == KEY_MAX marks an invalid slot.
+struct SelRet {
+    u64 lk;
+    int cnt;
+};
+__device__ __noinline__ SelRet knn_select_slow(u64 k0, u64 k1, u64 k2, u64 k3, u64 k4, u64 k5, u64 k6, u64 k7,
+                                               u64 lk, int cnt, u64* q) {
+    const int lane = threadIdx.x & 31;
+    const u64 kv[8] = {k0, k1, k2, k3, k4, k5, k6, k7};
+    u64 tau = __shfl_sync(FULL, lk, 15);
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        u64 key = KEY_MAX;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) key = (jj == j) ? kv[jj] : key;
+        bool ok = key < tau;
+        unsigned m = __ballot_sync(FULL, ok);
+        if (m == 0) continue;
+        if (cnt + __popc(m) > QCAP) {
+            lk = knn_flush(lk, q, cnt);
+            cnt = 0;
+            tau = __shfl_sync(FULL, lk, 15);
+            ok = key < tau;
+            m = __ballot_sync(FULL, ok);
+        }
+        if (ok) q[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+        cnt += __popc(m);
+    }
+    __syncwarp();
+    return SelRet{lk, cnt};
+}
 
 template <int MODE, int CPL>
 __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) {
@@ -368,8 +412,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     __shared__ __align__(16) float sbuf[BUF_FLOATS];
     __shared__ int sIdx[QT][LS_KNN_K];
     __shared__ float sDist[(MODE == MODE_KNN_ONLY) ? QT : 1][LS_KNN_K];
-    __shared__ float sQd[8][8][QCAP];  // [warp][query][slot] candidate queues
-    __shared__ int sQi[8][8][QCAP];
+    __shared__ u64 sQ[8][8][QCAP];  // [warp][query][slot] candidate queues (64-bit keys)
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int b = blockIdx.y;
@@ -417,13 +460,13 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
             for (int i = 0; i < 2; ++i) Qs[buf][(t >> 6) + 4 * i][t & 63] = qreg[i];
         };
 
-        // per query: the 32 best so far, ascending over the lanes (entry 15 is the running 16th)
-        float ld[8], acc[8][8];
-        int li[8], cnt[8];
+        // per query: the best keys so far, ascending over the lanes (entry 15 is the running 16th)
+        u64 lk[8];
+        float acc[8][8];
+        int cnt[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            ld[i] = FLT_MAX;
-            li[i] = 0x7fffffff;
+            lk[i] = KEY_MAX;
             cnt[i] = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
@@ -454,59 +497,61 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
                 }
                 const int tile = it / n_chunks, chunk = it - tile * n_chunks;
                 if (chunk == n_chunks - 1) {
-                    // ---- this tile's 8 x (32 lanes x 8) distances are final: keep what can still be
-                    //      among the 16 nearest.  Candidates below the running threshold are compacted
-                    //      (ballot + popc) into a per-query shared-memory queue; a full queue is merged
-                    //      into the sorted list with a warp bitonic network.
+                    // ---- this tile's 8 x (32 lanes x 8) distances are final.  Per query: candidates that beat
+                    //      the running 16th-best key are compacted into the query's shared-memory queue
+                    //      (8-bit pass mask per lane + one warp prefix sum, no per-slot ballots/branches);
+                    //      the queue is merged into the sorted list by a warp bitonic network when it holds
+                    //      more than 16 keys and after the last tile.  On the first tile the threshold
+                    //      starts from the 16th smallest of the 32 lane minima (an upper bound of the
+                    //      tile's 16th smallest distance).
                     const int sbase = tile * ST + lane * 4;
                     const bool last_tile = tile == n_tiles - 1;
+                    int sj[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sj[j] = sbase + (j < 4 ? j : 124 + j);
 #pragma unroll
                     for (int qi = 0; qi < 8; ++qi) {
-                        float tau = __shfl_sync(FULL, ld[qi], 15);
-                        int taui = __shfl_sync(FULL, li[qi], 15);
+                        u64 tau = __shfl_sync(FULL, lk[qi], 15);
                         if (tile == 0) {
-                            // 16th smallest of the 32 lane minima bounds the 16th smallest candidate
                             float mn = FLT_MAX;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                mn = (sbase + (j < 4 ? j : 124 + j) < Ns) ? fminf(mn, acc[qi][j]) : mn;
-                            tau = warp_kth16(mn, lane);
-                            taui = 0x7fffffff;
+                            for (int j = 0; j < 8; ++j) mn = sj[j] < Ns ? fminf(mn, acc[qi][j]) : mn;
+                            tau = make_key(warp_kth16_nl(mn), -1);  // index 0xffffffff: "<= distance" passes
                         }
-                        float* qd = sQd[w][qi];
-                        int* qx = sQi[w][qi];
-                        auto flush = [&]() {
-                            __syncwarp();
-                            const float bd = lane < cnt[qi] ? qd[lane] : FLT_MAX;
-                            const int bi = lane < cnt[qi] ? qx[lane] : 0x7fffffff;
-                            __syncwarp();
-                            merge_keep32(ld[qi], li[qi], bd, bi, lane);
-                            cnt[qi] = 0;
-                            tau = __shfl_sync(FULL, ld[qi], 15);
-                            taui = __shfl_sync(FULL, li[qi], 15);
-                        };
+                        u64 key[8];
+                        unsigned mask = 0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float d = acc[qi][j];
-                            const int s = sbase + (j < 4 ? j : 124 + j);
-                            bool ok = (s < Ns) && lex_less(d, s, tau, taui);
-                            unsigned m = __ballot_sync(FULL, ok);
-                            if (m) {
-                                if (cnt[qi] + __popc(m) > QCAP) {
-                                    flush();
-                                    ok = ok && lex_less(d, s, tau, taui);
-                                    m = __ballot_sync(FULL, ok);
-                                }
-                                if (ok) {
-                                    const int pos = cnt[qi] + __popc(m & ((1u << lane) - 1u));
-                                    qd[pos] = d;
-                                    qx[pos] = s;
-                                }
-                                cnt[qi] += __popc(m);
-                            }
+                            key[j] = sj[j] < Ns ? make_key(acc[qi][j], sj[j]) : KEY_MAX;
+                            mask |= (key[j] < tau ? 1u : 0u) << j;
                             acc[qi][j] = 0.f;
                         }
-                        if (cnt[qi] > 16 || (last_tile && cnt[qi] > 0)) flush();
+                        const int c = __popc(mask);
+                        int incl = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int v = __shfl_up_sync(FULL, incl, o);
+                            incl += lane >= o ? v : 0;
+                        }
+                        const int total = __shfl_sync(FULL, incl, 31);
+                        u64* q = sQ[w][qi];
+                        if (cnt[qi] + total > QCAP) {  // rare: queue overflow -> slot-by-slot with flushes
+                            const SelRet r = knn_select_slow(key[0], key[1], key[2], key[3], key[4], key[5], key[6],
+                                                             key[7], lk[qi], cnt[qi], q);
+                            lk[qi] = r.lk;
+                            cnt[qi] = r.cnt;
+                        } else {
+                            int pos = cnt[qi] + incl - c;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if ((mask >> j) & 1u) q[pos++] = key[j];
+                            }
+                            cnt[qi] += total;
+                        }
+                        if (cnt[qi] > 16 || (last_tile && cnt[qi] > 0)) {
+                            lk[qi] = knn_flush(lk[qi], q, cnt[qi]);
+                            cnt[qi] = 0;
+                        }
                     }
                 }
             }
@@ -518,8 +563,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
         if (warp_on && lane < LS_KNN_K) {
 #pragma unroll
             for (int qi = 0; qi < 8; ++qi) {
-                sIdx[w * 8 + qi][lane] = min(li[qi], Ns - 1);  // NaN features: stay in bounds
-                if (MODE == MODE_KNN_ONLY) sDist[w * 8 + qi][lane] = ld[qi];
+                sIdx[w * 8 + qi][lane] = min(key_idx(lk[qi]) & 0x7fffffff, Ns - 1);  // stay in bounds on NaN input
+                if (MODE == MODE_KNN_ONLY) sDist[w * 8 + qi][lane] = key_dist(lk[qi]);
             }
         }
     }
@@ -542,7 +587,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     }
 
     // ---------------------------------------------------------------------- phase 2: EdgeConv
-    const int Co = a.Co;
+    constexpr int Co = 32 * CPL;  // compile-time: gather offsets become immediates
     const float oms = a.oms;
     const size_t ostride = (size_t)3 * Nd;  // floats between output channels
 
@@ -590,7 +635,7 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     }
 
     const float* Ps = a.psrc + (size_t)b * Ns * a.row_s;
-    const int C3 = 3 * Co;  // floats per part
+    constexpr int C3 = 3 * Co;  // floats per part
 
     if (MODE == MODE_MEAN) {
         for (int ql = w; ql < nq; ql += 8) {
@@ -750,16 +795,20 @@ __global__ void __launch_bounds__(256) k_knn_small(const float* __restrict__ src
             }
         }
     }
-    float ad = lane < Ns ? acc[0] : FLT_MAX;
-    int ai = lane < Ns ? lane : 0x7fffffff;
-    bitonic_sort32(ad, ai, lane, false);
+    u64 lk = lane < Ns ? make_key(acc[0], lane) : KEY_MAX;
+    bitonic_sort32(lk, lane, false);
 #pragma unroll
     for (int j = 1; j < 4; ++j) {
         if (32 * j < Ns) {  // warp-uniform
             const int s = lane + 32 * j;
-            merge_keep32(ad, ai, s < Ns ? acc[j] : FLT_MAX, s < Ns ? s : 0x7fffffff, lane);
+            u64 bk = s < Ns ? make_key(acc[j], s) : KEY_MAX;
+            bitonic_sort32(bk, lane, true);
+            lk = bk < lk ? bk : lk;
+            bitonic_merge32(lk, lane);
         }
     }
+    const int ai = key_idx(lk) & 0x7fffffff;
+    const float ad = key_dist(lk);
     if (lane < LS_KNN_K) {
         idx_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = min(ai, Ns - 1);
         if (dist_out) dist_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = ad;
