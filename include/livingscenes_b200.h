@@ -34,7 +34,7 @@ extern "C" {
 #define LS_API
 #endif
 
-#define LS_ABI_VERSION 1
+#define LS_ABI_VERSION 2
 #define LS_MAX_LAYERS 8
 #define LS_KNN_K 16          /* num_knn of the shipped model (model_config.yaml:165) */
 #define LS_HEAD_C 16         /* atten_multi_head_c (model_config.yaml:143)           */
@@ -77,6 +77,11 @@ typedef struct ls_enc_layer_desc {
      * for the [:, c_out:] columns that multiply the instance mean (vec_dgcnn_atten.py:222-225)   */
     const float* w_g1;
     const float* w_g2;
+    /* optional (NULL = FP32 SIMT GEMM): w_src / w_dst / w_g1 packed by ls_tc_pack_weights for the
+     * tcgen05 3xTF32 tensor-core GEMM */
+    const float* w_src_tc;
+    const float* w_dst_tc;
+    const float* w_g1_tc;
 } ls_enc_layer_desc;
 
 typedef struct ls_encoder_desc {
@@ -95,6 +100,7 @@ typedef struct ls_encoder_desc {
     const float* w_short;    /* [c_dim]    fc_center.shortcut.weight                              */
     float w_act2;            /* fc_center.act2.lin_dir.weight (1x1)                               */
     int32_t _pad;
+    const float* w_conv_c_tc; /* optional: w_conv_c packed by ls_tc_pack_weights                          */
 } ls_encoder_desc;
 
 typedef struct ls_encoder_io {
@@ -133,6 +139,18 @@ LS_API int ls_encoder_forward(const ls_encoder_desc* desc, const ls_encoder_io* 
 LS_API int ls_profile_enable(int32_t on);
 LS_API int ls_profile_read(int32_t* stage, int32_t* layer, float* ms, int32_t max_entries, int32_t* n_entries);
 LS_API int64_t ls_kernel_launches(void);
+
+/* ------------------------------------------------------------------------------------------
+ * VecLinear.forward (vec_layers.py:121-134) as a stand-alone op, and the weight packing of the
+ * tensor-core path.  out[b][r][n] = sum_k W[r][k] X[b][k][n]  (X: [B,K,n], n = 3*points, channel-major).
+ * `packed` = NULL runs the FP32 SIMT GEMM; otherwise the tcgen05 3xTF32 GEMM (fp32-accurate: every
+ * operand is split into TF32 hi + lo parts, three MMAs accumulate in one fp32 TMEM tile).
+ * ------------------------------------------------------------------------------------------ */
+LS_API int ls_tc_packed_floats(int32_t R, int32_t K, size_t* n_floats);
+LS_API int ls_tc_pack_weights(const float* W, int32_t R, int32_t K, int32_t ldw, float* packed, void* stream);
+LS_API int ls_vn_linear(const float* W, const float* packed, const float* X, float* out, int32_t R, int32_t K,
+                        int32_t ldw, int32_t B, int32_t n, void* stream);
+LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 path where packed weights exist */
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone graph ops (the pytorch3d boundary of the reference)
@@ -198,6 +216,7 @@ typedef struct ls_decoder_desc {
     const float* w4_zinv;  /* [hidden][latent] columns of layer latent_in that multiply z_inv     */
     int32_t out_dims[12];  /* 768,768,768,255,768,768,768,768,1                                   */
     int32_t in_dims[12];   /* K of each GEMM (un-padded): 257,768,768,768,512,768,768,768,768     */
+    const float* w_tc[12]; /* optional: w[l] packed by ls_tc_pack_weights (layers 0..7)                  */
 } ls_decoder_desc;
 
 LS_API int ls_sdf_workspace_bytes(const ls_decoder_desc* desc, int32_t B, int32_t M, size_t* bytes);

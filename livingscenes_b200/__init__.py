@@ -14,12 +14,12 @@ from .encoder import VecDGCNN_att
 from .matcher_new import nn_matcher, nn_matcher_batched, sequential_matcher, sequential_matcher_batched
 from .model_utils import Shape_Prior, extract_checkpoint, slice_code_dict
 from .more_solver import More_Solver
-from .ops import farthest_point_sample, knn_points, sample_farthest_points
+from .ops import farthest_point_sample, knn_points, sample_farthest_points, vn_linear
 from .pose_estimation import kabsch_from_codes, kabsch_transformation_estimation, rotation_error, translation_error
 
 __all__ = [
     "Shape_Prior", "VecDGCNN_att", "DeepSDF_Decoder", "FieldWrapper", "More_Solver",
     "sequential_matcher", "sequential_matcher_batched", "nn_matcher", "nn_matcher_batched",
     "kabsch_transformation_estimation", "kabsch_from_codes", "rotation_error", "translation_error",
-    "knn_points", "sample_farthest_points", "farthest_point_sample", "extract_checkpoint", "slice_code_dict",
+    "knn_points", "sample_farthest_points", "vn_linear", "farthest_point_sample", "extract_checkpoint", "slice_code_dict",
 ]

@@ -29,6 +29,7 @@ class EncLayerDesc(C.Structure):
         ("attention", C.c_int32), ("global_conv", C.c_int32), ("_pad", C.c_int32),
         ("w0", C.c_void_p), ("w_src", C.c_void_p), ("w_dst", C.c_void_p),
         ("w_g1", C.c_void_p), ("w_g2", C.c_void_p),
+        ("w_src_tc", C.c_void_p), ("w_dst_tc", C.c_void_p), ("w_g1_tc", C.c_void_p),
     ]
 
 
@@ -39,6 +40,7 @@ class EncoderDesc(C.Structure):
         ("layers", EncLayerDesc * LS_MAX_LAYERS),
         ("w_conv_c", C.c_void_p), ("w_inv_t", C.c_void_p), ("w_fc0_t", C.c_void_p),
         ("w_lin1", C.c_void_p), ("w_short", C.c_void_p), ("w_act2", C.c_float), ("_pad", C.c_int32),
+        ("w_conv_c_tc", C.c_void_p),
     ]
 
 
@@ -60,6 +62,7 @@ class DecoderDesc(C.Structure):
         ("w", C.c_void_p * 12), ("b", C.c_void_p * 12),
         ("w0_zinv", C.c_void_p), ("w4_zinv", C.c_void_p),
         ("out_dims", C.c_int32 * 12), ("in_dims", C.c_int32 * 12),
+        ("w_tc", C.c_void_p * 12),
     ]
 
 
@@ -71,6 +74,11 @@ _PROTOS = {
     "ls_kernel_launches": (C.c_int64, []),
     "ls_encoder_workspace_bytes": (C.c_int, [C.POINTER(EncoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "ls_encoder_forward": (C.c_int, [C.POINTER(EncoderDesc), C.POINTER(EncoderIO), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ls_tc_packed_floats": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_tc_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ls_vn_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_int32, C.c_void_p]),
+    "ls_set_tensor_cores": (C.c_int, [C.c_int32]),
     "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_fps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_match_workspace_bytes": (C.c_int, [c_i32_p, c_i32_p, C.c_int32, C.POINTER(C.c_size_t)]),
@@ -152,3 +160,22 @@ def profile_read():
 
 def kernel_launches() -> int:
     return int(lib().ls_kernel_launches())
+
+
+def set_tensor_cores(on: bool) -> None:
+    """Route the packed-weight GEMMs through the tcgen05 3xTF32 kernel (default) or the FP32 SIMT kernel."""
+    check(lib().ls_set_tensor_cores(int(on)), "ls_set_tensor_cores")
+
+
+def tc_pack(weight_dev: torch.Tensor) -> torch.Tensor:
+    """Pack a row-major [R, ldw] fp32 device matrix (true K = its column count) for the tcgen05 GEMM."""
+    assert weight_dev.is_cuda and weight_dev.dtype == torch.float32 and weight_dev.dim() == 2
+    w = weight_dev.contiguous()
+    R, K = w.shape
+    n = C.c_size_t(0)
+    check(lib().ls_tc_packed_floats(R, K, C.byref(n)), "ls_tc_packed_floats")
+    out = torch.empty(n.value, dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib().ls_tc_pack_weights(w.data_ptr(), R, K, K, out.data_ptr(), stream_ptr(w.device)), "ls_tc_pack_weights")
+    out._ls_keep = w
+    return out

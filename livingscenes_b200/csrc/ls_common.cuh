@@ -81,6 +81,7 @@ __device__ __forceinline__ void vn_act(float q0, float q1, float q2, float k0, f
 // ---- GEMM launcher shared by the encoder and the SDF decoder (ls_gemm.cu) -------------------
 struct GemmArgs {
     const float* W;   // [R][ldw] row-major, ldw >= K, ldw % 4 == 0, zero padded beyond K
+    const float* Wtc; // optional: the same weights packed by tc_pack_weights (tcgen05 3xTF32 path)
     const float* X;   // element (b, k, n) at X[b*x_sb + k*x_sk + n]
     float* out;
     int R, K, ldw;
@@ -97,6 +98,13 @@ struct GemmArgs {
     int bias_axis;
     int relu;
 };
-int launch_gemm(const GemmArgs& a, cudaStream_t st);
+int launch_gemm(const GemmArgs& a, cudaStream_t st);       // dispatches to the tcgen05 path when possible
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);
+// tcgen05 3xTF32 path (ls_gemm_tc.cu)
+size_t tc_packed_floats(int R, int K);
+int tc_pack_weights(const float* W, int R, int K, int ldw, float* packed, cudaStream_t st);
+bool gemm_tc_supported(const GemmArgs& a);
+int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st);
+extern bool g_use_tensor_cores;
 
 }  // namespace ls

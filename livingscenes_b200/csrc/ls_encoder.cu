@@ -350,6 +350,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             g.c_out = Co;
             // source table
             g.W = L.w_src;
+            g.Wtc = L.w_src_tc;
             g.R = r_src;
             g.X = src_f;
             g.n_per_b = 3 * Ns;
@@ -361,6 +362,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             if (rc != LS_OK) return rc;
             // dst table
             g.W = L.w_dst;
+            g.Wtc = L.w_dst_tc;
             g.R = r_dst;
             g.X = dst_f;
             g.n_per_b = 3 * Nd;
@@ -385,6 +387,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             LS_CHECK_LAUNCH("k_mean_bias");
             GemmArgs g{};
             g.W = L.w_g1;
+            g.Wtc = L.w_g1_tc;
             g.R = 2 * Co;
             g.K = Co;
             g.ldw = Co;
@@ -421,6 +424,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         const int Cl = d->layers[last].c_out, Nl = p.n_dst[last], C = d->c_dim;
         GemmArgs g{};
         g.W = d->w_conv_c;
+        g.Wtc = d->w_conv_c_tc;
         g.R = C + 1;
         g.K = Cl;
         g.ldw = Cl;
@@ -461,6 +465,38 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         LS_CHECK_LAUNCH("k_head");
     }
     return LS_OK;
+}
+
+int ls_tc_packed_floats(int32_t R, int32_t K, size_t* n_floats) {
+    LS_REQUIRE(n_floats && R > 0 && K > 0, "bad arguments");
+    *n_floats = tc_packed_floats(R, K);
+    return LS_OK;
+}
+int ls_tc_pack_weights(const float* W, int32_t R, int32_t K, int32_t ldw, float* packed, void* stream) {
+    return tc_pack_weights(W, R, K, ldw, packed, static_cast<cudaStream_t>(stream));
+}
+int ls_set_tensor_cores(int32_t on) {
+    ls::g_use_tensor_cores = on != 0;
+    return LS_OK;
+}
+int ls_vn_linear(const float* W, const float* packed, const float* X, float* out, int32_t R, int32_t K, int32_t ldw,
+                 int32_t B, int32_t n, void* stream) {
+    LS_REQUIRE(W && X && out && R > 0 && K > 0 && B > 0 && n > 0, "bad arguments");
+    GemmArgs g{};
+    g.W = W;
+    g.Wtc = packed;
+    g.R = R;
+    g.K = K;
+    g.ldw = ldw;
+    g.B = B;
+    g.n_per_b = n;
+    g.X = X;
+    g.x_sb = (long long)K * n;
+    g.x_sk = n;
+    g.out = out;
+    g.o_sb = (long long)R * n;
+    g.o_sr = n;
+    return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
 int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns,

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm(const GemmArgs a) {
     }
 }
 
-int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+int launch_gemm_simt(const GemmArgs& a, cudaStream_t st) {
     LS_REQUIRE(a.ldw % 8 == 0 && a.ldw >= a.K, "gemm: ldw must be a multiple of 8 and >= K");
     LS_REQUIRE(a.R > 0 && a.K > 0 && a.B > 0 && a.n_per_b > 0, "gemm: empty problem");
     LS_REQUIRE((reinterpret_cast<uintptr_t>(a.W) & 15) == 0, "gemm: W must be 16-byte aligned");
@@ -150,6 +150,13 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
         k_gemm<false><<<grid, GEMM_THREADS, 0, st>>>(a);
     LS_CHECK_LAUNCH("k_gemm");
     return LS_OK;
+}
+
+bool g_use_tensor_cores = true;
+
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+    if (g_use_tensor_cores && a.Wtc != nullptr && gemm_tc_supported(a)) return launch_gemm_tc(a, a.Wtc, st);
+    return launch_gemm_simt(a, st);
 }
 
 }  // namespace ls

@@ -1,0 +1,330 @@
+// tcgen05 (5th-gen tensor core) GEMM with fp32-accurate 3xTF32 arithmetic, accumulators in TMEM.
+//
+//     C[r, (b,n)] = sum_k W[r,k] * X[b,k,n]          (same contract as ls_gemm.cu)
+//
+// Every fp32 operand is split x = hi + lo with hi = x rounded to the nearest TF32 number and lo = x - hi
+// (exact in fp32); three MMAs  lo*hi + hi*lo + hi*hi  accumulate in one fp32 TMEM tile.  SURVEY.md 7.1
+// fact 2: this keeps all 7 kNN graphs identical to the fp32 reference while single-pass TF32 does not.
+//
+// One CTA (128 threads) = one 128(rows) x 128(columns) output tile:
+//   * weights are pre-split and pre-tiled by k_tc_pack_weights into the exact canonical UMMA smem image
+//     (K-major, no swizzle: [kcore][mgroup][8 rows][4 k]); a k-block is one contiguous 16 KB copy;
+//   * activations are read as float4 along the contiguous column axis, transposed 4x4 in registers,
+//     split hi/lo and stored as the canonical K-major no-swizzle image ([kcore][ngroup][8 n][4 k]);
+//   * 2-stage ring: fence.proxy.async + __syncthreads publishes a stage, ONE thread issues the
+//     tcgen05.mma's (M=128, N=128, K=8, kind::tf32) and tcgen05.commit's to the stage's mbarrier so the
+//     next use of that stage waits for the tensor core to have consumed it;
+//   * epilogue: each warp tcgen05.ld's its 32 TMEM lanes (= 32 weight rows) and stores either the
+//     point-major gather table (128 B coalesced across lanes) or the channel-major tensor (+bias, relu).
+// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#include "ls_common.cuh"
+
+namespace ls {
+namespace {
+
+constexpr int TM = 128, TN = 128, TKB = 16;          // tile rows, tile columns, k-block
+constexpr int TC_THREADS = 128, TC_STAGES = 2;
+constexpr int A_STAGE_FLOATS = TM * TKB;              // per hi or lo image: 2048 floats (8 KB)
+constexpr int B_STAGE_FLOATS = TKB * TN;              // 2048 floats (8 KB)
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// smem matrix descriptor (no swizzle): start address, leading / stride byte offsets (>>4), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+    return d;                 // layout_type (bits 61-63) = 0: SWIZZLE_NONE / interleave
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both operands K-major, N=128, M=128
+// (MN-major + SWIZZLE_NONE produced all-zero results in profiles/microbench/tc_probe.cu, K-major is verified)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((TN >> 3) << 17) |
+                           ((TM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TcShared {
+    float a[TC_STAGES][2][A_STAGE_FLOATS];  // [stage][hi/lo]
+    float b[TC_STAGES][2][B_STAGE_FLOATS];
+    long long col_base[TN];                 // output offset of every tile column (-1 = out of range)
+    int col_axis[TN];
+    long long col_bias[TN];
+    uint64_t bar_empty[TC_STAGES];
+    uint64_t bar_done;
+    uint32_t tmem_base;
+};
+
+template <bool PM>
+__global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const float* __restrict__ wpk, int n_kb) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcShared& sh = *reinterpret_cast<TcShared*>(smem_raw);
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int r0 = blockIdx.y * TM;
+    const long long c0 = (long long)blockIdx.x * TN;
+    const long long ncols = (long long)a.B * a.n_per_b;
+
+    // ---- one-time setup: barriers, TMEM allocation (warp 0), per-column output offsets
+    if (t == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) mbar_init(&sh.bar_empty[s], 1);
+        mbar_init(&sh.bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const long long j = c0 + t;  // TC_THREADS == TN
+        long long base = -1, boff = 0;
+        int axis = 0;
+        if (j < ncols) {
+            const long long b = j / a.n_per_b;
+            const int n = (int)(j - b * a.n_per_b);
+            axis = a.npts > 0 ? n / a.npts : 0;
+            if (PM) {
+                const int pt = n - axis * a.npts;
+                base = (b * a.npts + pt) * ((long long)a.R * 3) + (long long)axis * a.c_out;
+            } else {
+                base = b * a.o_sb + n;
+                boff = b * a.bias_sb + (a.bias_axis ? axis : 0);
+            }
+        }
+        sh.col_base[t] = base;
+        sh.col_axis[t] = axis;
+        sh.col_bias[t] = boff;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = sh.tmem_base;
+
+    const float* wtile = wpk + (size_t)blockIdx.y * n_kb * (2 * A_STAGE_FLOATS);
+
+    for (int kb = 0; kb < n_kb; ++kb) {
+        const int stage = kb % TC_STAGES;
+        if (kb >= TC_STAGES) mbar_wait(&sh.bar_empty[stage], ((kb / TC_STAGES) - 1) & 1);
+        // weights: contiguous 16 KB image (hi then lo) -> smem
+        {
+            const float4* src = reinterpret_cast<const float4*>(wtile + (size_t)kb * (2 * A_STAGE_FLOATS));
+            float4* dst = reinterpret_cast<float4*>(&sh.a[stage][0][0]);
+#pragma unroll
+            for (int i = 0; i < (2 * A_STAGE_FLOATS / 4) / TC_THREADS; ++i) dst[t + i * TC_THREADS] = __ldg(src + t + i * TC_THREADS);
+        }
+        // activations: warp w owns k-core w (4 k rows), lane owns 4 consecutive columns.  Four coalesced
+        // float4 loads give a 4(k) x 4(n) block per thread; its transpose is four 16-byte core-matrix rows
+        // (one per column) of the canonical K-major image [kcore][ngroup][8 n][4 k].  The four stores are
+        // issued in a lane-rotated order so that each quarter-warp hits 8 distinct 16-byte bank groups.
+        {
+            const long long j = c0 + lane * 4;
+            float4 v[4];
+            bool col_ok = j < ncols;
+            long long xoff = 0;
+            if (col_ok) {
+                const long long b = j / a.n_per_b;
+                xoff = b * a.x_sb + (j - b * a.n_per_b);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k = kb * TKB + w * 4 + r;
+                v[r] = (col_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(a.X + xoff + (long long)k * a.x_sk))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int i = (s4 + (lane >> 1)) & 3;  // which of the thread's 4 columns goes out in this step
+                float4 c;
+                c.x = i == 0 ? v[0].x : (i == 1 ? v[0].y : (i == 2 ? v[0].z : v[0].w));
+                c.y = i == 0 ? v[1].x : (i == 1 ? v[1].y : (i == 2 ? v[1].z : v[1].w));
+                c.z = i == 0 ? v[2].x : (i == 1 ? v[2].y : (i == 2 ? v[2].z : v[2].w));
+                c.w = i == 0 ? v[3].x : (i == 1 ? v[3].y : (i == 2 ? v[3].z : v[3].w));
+                float4 hi, lo;
+                // round to nearest TF32 (magnitude + half ulp, then clear 13 bits): lo = x - hi is exact and
+                // signed, so the tensor core's truncation of lo does not accumulate a bias over K
+                hi.x = __uint_as_float((__float_as_uint(c.x) + 0x1000u) & 0xffffe000u);
+                hi.y = __uint_as_float((__float_as_uint(c.y) + 0x1000u) & 0xffffe000u);
+                hi.z = __uint_as_float((__float_as_uint(c.z) + 0x1000u) & 0xffffe000u);
+                hi.w = __uint_as_float((__float_as_uint(c.w) + 0x1000u) & 0xffffe000u);
+                lo.x = c.x - hi.x;
+                lo.y = c.y - hi.y;
+                lo.z = c.z - hi.z;
+                lo.w = c.w - hi.w;
+                const int n = lane * 4 + i;
+                const int off = ((w * (TN / 8) + (n >> 3)) * 8 + (n & 7)) * 4;
+                *reinterpret_cast<float4*>(&sh.b[stage][0][off]) = hi;
+                *reinterpret_cast<float4*>(&sh.b[stage][1][off]) = lo;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+        __syncthreads();
+        if (t == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(&sh.a[stage][0][0]), a_lo = smem_u32(&sh.a[stage][1][0]);
+            const uint32_t b_hi = smem_u32(&sh.b[stage][0][0]), b_lo = smem_u32(&sh.b[stage][1][0]);
+#pragma unroll
+            for (int s = 0; s < TKB / 8; ++s) {
+                // A: K-major, cores of 8 rows x 16 B; m-groups 128 B apart (SBO), k-cores 2048 B apart (LBO)
+                const uint64_t dah = make_desc(a_hi + s * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                const uint64_t dal = make_desc(a_lo + s * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                // B: K-major as well (the loader transposes): n-groups 128 B apart, k-cores 2048 B apart
+                const uint64_t dbh = make_desc(b_hi + s * 2 * (TN / 8) * 128, (TN / 8) * 128, 128);
+                const uint64_t dbl = make_desc(b_lo + s * 2 * (TN / 8) * 128, (TN / 8) * 128, 128);
+                umma_tf32(tmem_d, dal, dbh, (kb | s) != 0);
+                umma_tf32(tmem_d, dah, dbl, 1);
+                umma_tf32(tmem_d, dah, dbh, 1);
+            }
+            umma_commit(&sh.bar_empty[stage]);  // frees this smem stage when the MMAs have read it
+            if (kb == n_kb - 1) umma_commit(&sh.bar_done);
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> global
+    mbar_wait(&sh.bar_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = r0 + w * 32 + lane;  // TMEM lane == tile row
+    const bool row_ok = r < a.R;
+    long long row_off = 0;
+    if (PM) {
+        const int part = row_ok ? r / a.c_out : 0;
+        row_off = (long long)part * 3 * a.c_out + (r - part * a.c_out);
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < TN; cc += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(w * 32) << 16) + (uint32_t)cc;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const long long base = sh.col_base[cc + j];
+                if (base < 0) continue;
+                float val = __uint_as_float(v[j]);
+                if (PM) {
+                    a.out[base + row_off] = val;  // lanes = consecutive channels: 128 B coalesced
+                } else {
+                    if (a.bias) val += __ldg(a.bias + sh.col_bias[cc + j] + (long long)r * a.bias_sr);
+                    if (a.relu) val = fmaxf(val, 0.f);
+                    a.out[base + (long long)r * a.o_sr] = val;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// W [R][ldw] row-major -> per (m-tile, k-block): hi image then lo image, each [kcore 4][mgroup 16][8 rows][4 k]
+__global__ void k_tc_pack_weights(const float* __restrict__ W, int R, int K, int ldw, float* __restrict__ out, int n_kb) {
+    const int mt = blockIdx.y, kb = blockIdx.x;
+    float* dst = out + ((size_t)mt * n_kb + kb) * (2 * A_STAGE_FLOATS);
+    for (int e = threadIdx.x; e < A_STAGE_FLOATS; e += blockDim.x) {
+        const int kk = e & 3, row8 = (e >> 2) & 7, mg = (e >> 5) & 15, kc = e >> 9;
+        const int r = mt * TM + mg * 8 + row8, k = kb * TKB + kc * 4 + kk;
+        const float x = (r < R && k < K) ? W[(size_t)r * ldw + k] : 0.f;
+        // round-to-nearest-even to TF32 for the hi part (the tensor core truncates, so hi must be exact TF32)
+        uint32_t u = __float_as_uint(x);
+        uint32_t h = (u + 0x00000fffu + ((u >> 13) & 1u)) & 0xffffe000u;
+        if ((u & 0x7f800000u) == 0x7f800000u) h = u & 0xffffe000u;  // inf / nan: no rounding carry
+        const float hi = __uint_as_float(h);
+        dst[e] = hi;
+        dst[A_STAGE_FLOATS + e] = x - hi;
+    }
+}
+
+}  // namespace
+
+size_t tc_packed_floats(int R, int K) {
+    const size_t mt = (R + TM - 1) / TM, kb = (K + TKB - 1) / TKB;
+    return mt * kb * 2 * A_STAGE_FLOATS;
+}
+
+int tc_pack_weights(const float* W, int R, int K, int ldw, float* packed, cudaStream_t st) {
+    LS_REQUIRE(W && packed && R > 0 && K > 0 && ldw >= K, "tc_pack_weights: bad arguments");
+    const int n_kb = (K + TKB - 1) / TKB;
+    dim3 grid(n_kb, (R + TM - 1) / TM);
+    k_tc_pack_weights<<<grid, 256, 0, st>>>(W, R, K, ldw, packed, n_kb);
+    LS_CHECK_LAUNCH("k_tc_pack_weights");
+    return LS_OK;
+}
+
+bool gemm_tc_supported(const GemmArgs& a) {
+    // float4 activation loads: 4-column groups must not straddle instances and must be 16 B aligned
+    if (a.n_per_b % 4 != 0 || a.x_sb % 4 != 0 || a.x_sk % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.X) & 15) != 0) return false;
+    return true;
+}
+
+int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
+    LS_REQUIRE(packed != nullptr, "gemm_tc: packed weights missing");
+    LS_REQUIRE(gemm_tc_supported(a), "gemm_tc: unsupported activation geometry");
+    LS_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "gemm_tc: packed weights must be 16-byte aligned");
+    if (a.point_major)
+        LS_REQUIRE(a.c_out % 32 == 0 && a.R % a.c_out == 0 && a.npts > 0 && a.n_per_b == 3 * a.npts,
+                   "gemm_tc: bad point-major geometry");
+    const long long ncols = (long long)a.B * a.n_per_b;
+    const int n_kb = (a.K + TKB - 1) / TKB;
+    dim3 grid((unsigned)((ncols + TN - 1) / TN), (unsigned)((a.R + TM - 1) / TM));
+    const size_t smem = sizeof(TcShared) + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (a.point_major)
+        k_gemm_tc<true><<<grid, TC_THREADS, smem, st>>>(a, packed, n_kb);
+    else
+        k_gemm_tc<false><<<grid, TC_THREADS, smem, st>>>(a, packed, n_kb);
+    LS_CHECK_LAUNCH("k_gemm_tc");
+    return LS_OK;
+}
+
+}  // namespace ls

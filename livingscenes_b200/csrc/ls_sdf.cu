@@ -138,6 +138,7 @@ int ls_sdf_decode(const ls_decoder_desc* d, const float* query, const float* z_s
         auto layer = [&](int l, const float* X, int K, float* out, int R, const float* bvec, long long bias_sb) {
             GemmArgs g{};
             g.W = d->w[l];
+            g.Wtc = d->w_tc[l];
             g.R = R;
             g.K = K;
             g.ldw = (K + 7) & ~7;

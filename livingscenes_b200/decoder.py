@@ -104,7 +104,14 @@ class DeepSDF_Decoder(nn.Module):
             d.in_dims[l] = mats[l].shape[1] if l in mats else self.in_dims[l]
         d.w0_zinv = base + 4 * offs["w0_zinv"]
         d.w4_zinv = base + 4 * offs["w4_zinv"]
-        self._packed = {"ver": ver, "blob": blob, "desc": d}
+        tc = {}
+        for l in range(8):
+            K = d.in_dims[l]
+            Kp = (K + 7) // 8 * 8
+            wv = blob[offs[f"w{l}"]:offs[f"w{l}"] + self.out_dims[l] * Kp].view(self.out_dims[l], Kp)[:, :K]
+            tc[l] = _lib.tc_pack(wv.contiguous())
+            d.w_tc[l] = tc[l].data_ptr()
+        self._packed = {"ver": ver, "blob": blob, "desc": d, "tc": tc}
         return self._packed
 
     @torch.no_grad()

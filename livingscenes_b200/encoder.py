@@ -222,7 +222,20 @@ class VecDGCNN_att(nn.Module):
         if self.center_pred:
             desc.w_fc0_t, desc.w_lin1, desc.w_short = P("w_fc0_t"), P("w_lin1"), P("w_short")
             desc.w_act2 = float(self.fc_center.act2.lin_dir.weight.detach().reshape(-1)[0])
-        self._packed = {"ver": ver, "blob": blob, "desc": desc}
+        # tensor-core copies of the GEMM weights (hi/lo TF32 split, UMMA smem image), packed on the device
+        tc = {}
+        views = lambda k: blob[offs[k]:offs[k] + folded[k].numel()].view(folded[k].shape)
+        for i in range(1, self.num_layers):
+            L = desc.layers[i]
+            tc[f"l{i}.src"] = _lib.tc_pack(views(f"l{i}.w_src"))
+            tc[f"l{i}.dst"] = _lib.tc_pack(views(f"l{i}.w_dst"))
+            L.w_src_tc, L.w_dst_tc = tc[f"l{i}.src"].data_ptr(), tc[f"l{i}.dst"].data_ptr()
+            if L.global_conv:
+                tc[f"l{i}.g1"] = _lib.tc_pack(views(f"l{i}.w_g1"))
+                L.w_g1_tc = tc[f"l{i}.g1"].data_ptr()
+        tc["conv_c"] = _lib.tc_pack(views("w_conv_c"))
+        desc.w_conv_c_tc = tc["conv_c"].data_ptr()
+        self._packed = {"ver": ver, "blob": blob, "desc": desc, "tc": tc}
         self._ws.clear()
         return self._packed
 

@@ -75,3 +75,25 @@ def sample_farthest_points(points: torch.Tensor, K: int = 50, random_start_point
         raise NotImplementedError("random_start_point is not built (the evals use n_init = 1, start index 0)")
     idx, out = farthest_point_sample(points.transpose(1, 2), K)
     return out.transpose(1, 2).to(points.dtype), idx
+
+
+@torch.no_grad()
+def vn_linear(weight: torch.Tensor, v: torch.Tensor, tensor_cores: bool = True) -> torch.Tensor:
+    """VecLinear.forward (vec_layers.py:121-134, so3, vector-only): weight [Co,Ci], v [B,Ci,3,...] ->
+    [B,Co,3,...].  ``tensor_cores`` selects the tcgen05 3xTF32 GEMM (fp32-accurate) or the FP32 SIMT GEMM."""
+    _lib.require_cuda(v, "v")
+    B, Ci = v.shape[0], v.shape[1]
+    Co = weight.shape[0]
+    x = v.detach().float().reshape(B, Ci, -1).contiguous()
+    n = x.shape[2]
+    Kp = (Ci + 7) // 8 * 8
+    w = torch.zeros(Co, Kp, device=v.device)
+    w[:, :Ci] = weight.detach().float()
+    out = torch.empty(B, Co, n, device=v.device)
+    packed = _lib.tc_pack(w[:, :Ci].contiguous()) if tensor_cores else None
+    with torch.cuda.device(v.device):
+        rc = _lib.lib().ls_vn_linear(w.data_ptr(), _lib.ptr(packed), x.data_ptr(), out.data_ptr(), Co, Ci, Kp, B, n,
+                                     _lib.stream_ptr(v.device))
+        _lib.check(rc, "ls_vn_linear")
+        _lib.launch_count += 1
+    return out.reshape(B, Co, *v.shape[2:])
