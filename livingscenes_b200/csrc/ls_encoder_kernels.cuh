@@ -407,7 +407,7 @@ template <int MODE, int CPL>
 __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) {
     // phase-1 tiles and phase-2 scratch share one buffer
     constexpr int TILE_FLOATS = 2 * DKC * (QT + ST);
-    constexpr int SR_FLOATS = (MODE == MODE_ATT) ? 8 * CPL * 32 : 0;
+    constexpr int SR_FLOATS = (MODE == MODE_ATT) ? 8 * (CPL > 4 ? CPL / 4 : 1) * LS_KNN_K * 8 : 0;
     constexpr int BUF_FLOATS = TILE_FLOATS > SR_FLOATS ? TILE_FLOATS : SR_FLOATS;
     __shared__ __align__(16) float sbuf[BUF_FLOATS];
     __shared__ int sIdx[QT][LS_KNN_K];
@@ -634,135 +634,210 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
         return;
     }
 
+    // ---- layers >= 1: gather form.  A lane owns 4 consecutive channels (one float4 per table part and
+    //      axis); LPP lanes cover one dst point, PPW points are processed per warp pass, and layers with
+    //      more than 128 channels walk CH chunks of 128.
     const float* Ps = a.psrc + (size_t)b * Ns * a.row_s;
     constexpr int C3 = 3 * Co;  // floats per part
+    constexpr int CG = Co / 4;
+    constexpr int LPP = CG < 32 ? CG : 32;
+    constexpr int PPW = 32 / LPP;
+    constexpr int CH = CG / LPP;
+    const int sub = lane / LPP, gl = lane % LPP;
+    auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
+    auto add4 = [](float4 x, float4 y) { return make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w); };
+    // VN leaky-ReLU on 4 channels at once: q[axis], k[axis] hold the 4 channels of one axis
+    auto act4 = [&](const float4* q, const float4* k, float4* o) {
+        vn_act(q[0].x, q[1].x, q[2].x, k[0].x, k[1].x, k[2].x, oms, o[0].x, o[1].x, o[2].x);
+        vn_act(q[0].y, q[1].y, q[2].y, k[0].y, k[1].y, k[2].y, oms, o[0].y, o[1].y, o[2].y);
+        vn_act(q[0].z, q[1].z, q[2].z, k[0].z, k[1].z, k[2].z, oms, o[0].z, o[1].z, o[2].z);
+        vn_act(q[0].w, q[1].w, q[2].w, k[0].w, k[1].w, k[2].w, oms, o[0].w, o[1].w, o[2].w);
+    };
+    auto store_out = [&](int c4, int n, const float4* v, float sc) {
+        float* o = a.out + ((size_t)b * Co + c4) * ostride + n;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+            o[(size_t)0 * ostride + ax * Nd] = v[ax].x * sc;
+            o[(size_t)1 * ostride + ax * Nd] = v[ax].y * sc;
+            o[(size_t)2 * ostride + ax * Nd] = v[ax].z * sc;
+            o[(size_t)3 * ostride + ax * Nd] = v[ax].w * sc;
+        }
+    };
 
     if (MODE == MODE_MEAN) {
-        for (int ql = w; ql < nq; ql += 8) {
+        for (int base = w * PPW; base < nq; base += 8 * PPW) {
+            const bool on = base + sub < nq;
+            const int ql = on ? base + sub : nq - 1;
             const int n = q0 + ql;
             const float* Pd = a.pdst + ((size_t)b * Nd + n) * a.row_d;
 #pragma unroll 1
-            for (int j = 0; j < CPL; ++j) {
-                const int c = j * 32 + lane;
-                const float dq0 = __ldg(Pd + c), dq1 = __ldg(Pd + Co + c), dq2 = __ldg(Pd + 2 * Co + c);
-                const float dk0 = __ldg(Pd + C3 + c), dk1 = __ldg(Pd + C3 + Co + c), dk2 = __ldg(Pd + C3 + 2 * Co + c);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int ch = 0; ch < CH; ++ch) {
+                const int c4 = (ch * LPP + gl) * 4;
+                float4 dq[3], dk[3], acc[3];
 #pragma unroll
-                for (int k = 0; k < LS_KNN_K; ++k) {
-                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + c;
-                    const float qx = __ldg(row) + dq0, qy = __ldg(row + Co) + dq1, qz = __ldg(row + 2 * Co) + dq2;
-                    const float kx = __ldg(row + C3) + dk0, ky = __ldg(row + C3 + Co) + dk1,
-                                kz = __ldg(row + C3 + 2 * Co) + dk2;
-                    float o0, o1, o2;
-                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
-                    a0 += o0;
-                    a1 += o1;
-                    a2 += o2;
+                for (int ax = 0; ax < 3; ++ax) {
+                    dq[ax] = ld4(Pd + ax * Co + c4);
+                    dk[ax] = ld4(Pd + C3 + ax * Co + c4);
+                    acc[ax] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                float* o = a.out + ((size_t)b * Co + c) * ostride + n;
-                o[0] = a0 * (1.f / LS_KNN_K);
-                o[Nd] = a1 * (1.f / LS_KNN_K);
-                o[2 * Nd] = a2 * (1.f / LS_KNN_K);
+#pragma unroll 4
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + c4;
+                    float4 q[3], kk[3], o[3];
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        q[ax] = add4(ld4(row + ax * Co), dq[ax]);
+                        kk[ax] = add4(ld4(row + C3 + ax * Co), dk[ax]);
+                    }
+                    act4(q, kk, o);
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) acc[ax] = add4(acc[ax], o[ax]);
+                }
+                if (on) store_out(c4, n, acc, 1.f / LS_KNN_K);
             }
         }
         return;
     }
 
     if (MODE == MODE_ATT) {
-        float* sR = sbuf + (size_t)w * CPL * 32;  // [CPL][32] per warp (phase-1 tiles are dead)
+        float* sR = sbuf + (size_t)w * (CH * LS_KNN_K * 8);  // [chunk][edge][head slot] per warp (tiles are dead)
         const float inv_sqrt = rsqrtf(3.f * (float)LS_HEAD_C);
-        for (int ql = w; ql < nq; ql += 8) {
+        const int hs = lane >> 2;  // 4 lanes x 4 channels = one 16-channel head
+        for (int base = w * PPW; base < nq; base += 8 * PPW) {
+            const bool on = base + sub < nq;
+            const int ql = on ? base + sub : nq - 1;
             const int n = q0 + ql;
             const float* Pd = a.pdst + ((size_t)b * Nd + n) * a.row_d;
-            // ---- |Q|: channel-norm of the activated query feature (cevn, vec_layers.py:24-31)
+            // ---- |Q| over all channels of the point (cevn, vec_layers.py:24-31)
             float ssum = 0.f;
 #pragma unroll 1
-            for (int j = 0; j < CPL; ++j) {
-                const int c = j * 32 + lane;
-                const float* pq = Pd + 4 * C3 + c;
-                float o0, o1, o2;
-                vn_act(__ldg(pq), __ldg(pq + Co), __ldg(pq + 2 * Co), __ldg(pq + C3), __ldg(pq + C3 + Co),
-                       __ldg(pq + C3 + 2 * Co), oms, o0, o1, o2);
-                ssum += fmaf(o2, o2, fmaf(o1, o1, o0 * o0));
+            for (int ch = 0; ch < CH; ++ch) {
+                const int c4 = (ch * LPP + gl) * 4;
+                float4 q[3], kk[3], o[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    q[ax] = ld4(Pd + 4 * C3 + ax * Co + c4);
+                    kk[ax] = ld4(Pd + 5 * C3 + ax * Co + c4);
+                }
+                act4(q, kk, o);
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax)
+                    ssum += o[ax].x * o[ax].x + o[ax].y * o[ax].y + o[ax].z * o[ax].z + o[ax].w * o[ax].w;
             }
-            ssum = warp_sum(ssum);
+#pragma unroll
+            for (int off = LPP / 2; off > 0; off >>= 1) ssum += __shfl_xor_sync(FULL, ssum, off);
             const float Lq = fmaxf(sqrtf(ssum), EPS_NRM);
 
-            // ---- pass A: K branch -> per-edge channel norm and per-head raw logits
+            // ---- pass A: K branch -> per-edge channel norm S[k] and per-head raw logits R[chunk][k]
             float S[LS_KNN_K];
 #pragma unroll
             for (int k = 0; k < LS_KNN_K; ++k) S[k] = 0.f;
 #pragma unroll 1
-            for (int j = 0; j < CPL; ++j) {
-                const int c = j * 32 + lane;
-                const float* pq = Pd + 4 * C3 + c;
-                float v0, v1, v2;
-                vn_act(__ldg(pq), __ldg(pq + Co), __ldg(pq + 2 * Co), __ldg(pq + C3), __ldg(pq + C3 + Co),
-                       __ldg(pq + C3 + 2 * Co), oms, v0, v1, v2);
-                const float ell = sqrtf(fmaf(v2, v2, fmaf(v1, v1, v0 * v0)));
-                const float ed = fmaxf(ell, EPS_NRM), fn = ell / Lq;
-                const float g0 = (v0 / ed) * fn, g1 = (v1 / ed) * fn, g2 = (v2 / ed) * fn;  // cevn(Q)
-                const float* pk = Pd + 2 * C3 + c;
-                const float dq0 = __ldg(pk), dq1 = __ldg(pk + Co), dq2 = __ldg(pk + 2 * Co);
-                const float dk0 = __ldg(pk + C3), dk1 = __ldg(pk + C3 + Co), dk2 = __ldg(pk + C3 + 2 * Co);
-                float Rj = 0.f;
+            for (int ch = 0; ch < CH; ++ch) {
+                const int c4 = (ch * LPP + gl) * 4;
+                float4 g[3];  // cevn(Q) of this lane's 4 channels
+                {
+                    float4 q[3], kk[3], o[3];
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        q[ax] = ld4(Pd + 4 * C3 + ax * Co + c4);
+                        kk[ax] = ld4(Pd + 5 * C3 + ax * Co + c4);
+                    }
+                    act4(q, kk, o);
+                    float f[4];
+                    const float e0 = sqrtf(o[0].x * o[0].x + o[1].x * o[1].x + o[2].x * o[2].x);
+                    const float e1 = sqrtf(o[0].y * o[0].y + o[1].y * o[1].y + o[2].y * o[2].y);
+                    const float e2 = sqrtf(o[0].z * o[0].z + o[1].z * o[1].z + o[2].z * o[2].z);
+                    const float e3 = sqrtf(o[0].w * o[0].w + o[1].w * o[1].w + o[2].w * o[2].w);
+                    f[0] = (e0 / Lq) / fmaxf(e0, EPS_NRM);
+                    f[1] = (e1 / Lq) / fmaxf(e1, EPS_NRM);
+                    f[2] = (e2 / Lq) / fmaxf(e2, EPS_NRM);
+                    f[3] = (e3 / Lq) / fmaxf(e3, EPS_NRM);
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax)
+                        g[ax] = make_float4(o[ax].x * f[0], o[ax].y * f[1], o[ax].z * f[2], o[ax].w * f[3]);
+                }
+                float4 dq[3], dk[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    dq[ax] = ld4(Pd + 2 * C3 + ax * Co + c4);
+                    dk[ax] = ld4(Pd + 3 * C3 + ax * Co + c4);
+                }
 #pragma unroll
                 for (int k = 0; k < LS_KNN_K; ++k) {
-                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + 2 * C3 + c;
-                    const float qx = __ldg(row) + dq0, qy = __ldg(row + Co) + dq1, qz = __ldg(row + 2 * Co) + dq2;
-                    const float kx = __ldg(row + C3) + dk0, ky = __ldg(row + C3 + Co) + dk1,
-                                kz = __ldg(row + C3 + 2 * Co) + dk2;
-                    float o0, o1, o2;
-                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
-                    S[k] += fmaf(o2, o2, fmaf(o1, o1, o0 * o0));
-                    float r = fmaf(o2, g2, fmaf(o1, g1, o0 * g0));
-                    r = half_sum(r);
-                    if ((lane & 15) == k) Rj = r;
+                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + 2 * C3 + c4;
+                    float4 q[3], kk[3], o[3];
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        q[ax] = add4(ld4(row + ax * Co), dq[ax]);
+                        kk[ax] = add4(ld4(row + C3 + ax * Co), dk[ax]);
+                    }
+                    act4(q, kk, o);
+                    float sk = 0.f, r = 0.f;
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        sk += o[ax].x * o[ax].x + o[ax].y * o[ax].y + o[ax].z * o[ax].z + o[ax].w * o[ax].w;
+                        r += o[ax].x * g[ax].x + o[ax].y * g[ax].y + o[ax].z * g[ax].z + o[ax].w * g[ax].w;
+                    }
+                    S[k] += sk;
+                    r += __shfl_xor_sync(FULL, r, 1);
+                    r += __shfl_xor_sync(FULL, r, 2);
+                    if ((lane & 3) == 0) sR[(ch * LS_KNN_K + k) * 8 + hs] = r;
                 }
-                sR[j * 32 + lane] = Rj;
             }
-            float Sme = 0.f;
+            // per-edge |K| over all channels of the point
 #pragma unroll
             for (int k = 0; k < LS_KNN_K; ++k) {
-                const float s = warp_sum(S[k]);
-                if ((lane & 15) == k) Sme = s;
-            }
-            const float Lk = fmaxf(sqrtf(Sme), EPS_NRM);
-            __syncwarp();
-#pragma unroll 1
-            for (int j = 0; j < CPL; ++j) {
-                const float logit = (sR[j * 32 + lane] / Lk) * inv_sqrt;
-                const float mx = half_max(logit);
-                const float e = expf(logit - mx);
-                const float den = half_sum(e);
-                sR[j * 32 + lane] = e / den;
+#pragma unroll
+                for (int off = LPP / 2; off > 0; off >>= 1) S[k] += __shfl_xor_sync(FULL, S[k], off);
+                S[k] = inv_sqrt / fmaxf(sqrtf(S[k]), EPS_NRM);  // logit scale of edge k
             }
             __syncwarp();
-            // ---- pass B: V branch, attention-weighted sum over the 16 edges
+            // ---- pass B: softmax over the 16 edges (in-thread, per head) and the weighted sum of V
 #pragma unroll 1
-            for (int j = 0; j < CPL; ++j) {
-                const int c = j * 32 + lane;
-                const float al = sR[j * 32 + lane];
-                const float dq0 = __ldg(Pd + c), dq1 = __ldg(Pd + Co + c), dq2 = __ldg(Pd + 2 * Co + c);
-                const float dk0 = __ldg(Pd + C3 + c), dk1 = __ldg(Pd + C3 + Co + c), dk2 = __ldg(Pd + C3 + 2 * Co + c);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            for (int ch = 0; ch < CH; ++ch) {
+                const int c4 = (ch * LPP + gl) * 4;
+                float al[LS_KNN_K];
+                float mx = -FLT_MAX;
 #pragma unroll
                 for (int k = 0; k < LS_KNN_K; ++k) {
-                    const float ak = __shfl_sync(FULL, al, (lane & 16) | k);
-                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + c;
-                    const float qx = __ldg(row) + dq0, qy = __ldg(row + Co) + dq1, qz = __ldg(row + 2 * Co) + dq2;
-                    const float kx = __ldg(row + C3) + dk0, ky = __ldg(row + C3 + Co) + dk1,
-                                kz = __ldg(row + C3 + 2 * Co) + dk2;
-                    float o0, o1, o2;
-                    vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
-                    a0 = fmaf(ak, o0, a0);
-                    a1 = fmaf(ak, o1, a1);
-                    a2 = fmaf(ak, o2, a2);
+                    al[k] = sR[(ch * LS_KNN_K + k) * 8 + hs] * S[k];
+                    mx = fmaxf(mx, al[k]);
                 }
-                float* o = a.out + ((size_t)b * Co + c) * ostride + n;
-                o[0] = a0;
-                o[Nd] = a1;
-                o[2 * Nd] = a2;
+                float den = 0.f;
+#pragma unroll
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    al[k] = expf(al[k] - mx);
+                    den += al[k];
+                }
+                const float rden = 1.f / den;
+                float4 dq[3], dk[3], acc[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    dq[ax] = ld4(Pd + ax * Co + c4);
+                    dk[ax] = ld4(Pd + C3 + ax * Co + c4);
+                    acc[ax] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < LS_KNN_K; ++k) {
+                    const float* row = Ps + (size_t)sIdx[ql][k] * a.row_s + c4;
+                    float4 q[3], kk[3], o[3];
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        q[ax] = add4(ld4(row + ax * Co), dq[ax]);
+                        kk[ax] = add4(ld4(row + C3 + ax * Co), dk[ax]);
+                    }
+                    act4(q, kk, o);
+                    const float ak = al[k] * rden;
+#pragma unroll
+                    for (int ax = 0; ax < 3; ++ax) {
+                        acc[ax].x = fmaf(ak, o[ax].x, acc[ax].x);
+                        acc[ax].y = fmaf(ak, o[ax].y, acc[ax].y);
+                        acc[ax].z = fmaf(ak, o[ax].z, acc[ax].z);
+                        acc[ax].w = fmaf(ak, o[ax].w, acc[ax].w);
+                    }
+                }
+                if (on) store_out(c4, n, acc, 1.f);
             }
             __syncwarp();
         }
