@@ -65,6 +65,28 @@ __device__ __forceinline__ float half_max(float v) {
     return v;
 }
 
+// Packed FP32 pairs (Blackwell FADD2 / FFMA2, PTX add/fma .f32x2): two IEEE-rounded fp32 operations per
+// issued instruction; results are bit-identical to the scalar form.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // VN leaky-ReLU on one 3-vector (vec_layers.py:241-268, so3 mode) in sqrt-free form:
 //   out = q + (lrelu(p) - p) * khat,  p = <q, khat>,  khat = k / max(|k|, 1e-12)
 //       = q - (1 - slope) * min(<q,k>, 0) / max(|k|^2, 1e-24) * k

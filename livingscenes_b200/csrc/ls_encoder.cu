@@ -182,8 +182,11 @@ int launch_fps(const FpsArgs& a, int B, cudaStream_t st) {
         int prev = l == 0 ? N : a.n_out[l - 1];
         LS_REQUIRE(a.n_out[l] >= 1 && a.n_out[l] <= prev, "fps: n_out must not exceed the number of points");
     }
+    // few warps, several points per thread: every selected point costs one block-wide arg-max, whose
+    // instruction count grows with the number of warps (each warp redoes the final reduction), so the
+    // kernel is issue-bound with many threads.  8 points per thread up to N = 8192.
     int T = 128;
-    while (T < 1024 && T * 2 <= N) T *= 2;  // ~1-2 points per thread for N <= 2048
+    while (T < 1024 && T * 8 < N) T *= 2;
     const int ppt = (N + T - 1) / T;
     const size_t smem = (size_t)(3 * N + 4 * a.n_out[0]) * sizeof(float);
 #define LS_FPS_CASE(P)                                                                              \

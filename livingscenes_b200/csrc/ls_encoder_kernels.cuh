@@ -462,14 +462,14 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
 
         // per query: the best keys so far, ascending over the lanes (entry 15 is the running 16th)
         u64 lk[8];
-        float acc[8][8];
+        f32x2_t acc2[8][4];  // squared distances of 8 queries x 8 sources, as 4 packed fp32 pairs per query
         int cnt[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             lk[i] = KEY_MAX;
             cnt[i] = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
         }
 
         g_load(0);
@@ -486,14 +486,17 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
                     const float4 sa = *reinterpret_cast<const float4*>(&Ss[buf][dd][lane * 4]);
                     const float4 sb = *reinterpret_cast<const float4*>(&Ss[buf][dd][128 + lane * 4]);
                     const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-                    const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                    const f32x2_t sp[4] = {pack2(sa.x, sa.y), pack2(sa.z, sa.w), pack2(sb.x, sb.y), pack2(sb.z, sb.w)};
+                    // acc += (q - s)^2 in the direct form, two sources per FADD2 / FFMA2
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i) {
+                        const f32x2_t qq = pack2(qv[i], qv[i]);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float df = qv[i] - sv[j];
-                            acc[i][j] = fmaf(df, df, acc[i][j]);
+                        for (int j = 0; j < 4; ++j) {
+                            const f32x2_t df = sub2(qq, sp[j]);
+                            acc2[i][j] = fma2(df, df, acc2[i][j]);
                         }
+                    }
                 }
                 const int tile = it / n_chunks, chunk = it - tile * n_chunks;
                 if (chunk == n_chunks - 1) {
@@ -511,20 +514,25 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
                     for (int j = 0; j < 8; ++j) sj[j] = sbase + (j < 4 ? j : 124 + j);
 #pragma unroll
                     for (int qi = 0; qi < 8; ++qi) {
+                        float acc[1][8];  // this query's 8 distances, unpacked
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            unpack2(acc2[qi][j], acc[0][2 * j], acc[0][2 * j + 1]);
+                            acc2[qi][j] = 0ull;
+                        }
                         u64 tau = __shfl_sync(FULL, lk[qi], 15);
                         if (tile == 0) {
                             float mn = FLT_MAX;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) mn = sj[j] < Ns ? fminf(mn, acc[qi][j]) : mn;
+                            for (int j = 0; j < 8; ++j) mn = sj[j] < Ns ? fminf(mn, acc[0][j]) : mn;
                             tau = make_key(warp_kth16_nl(mn), -1);  // index 0xffffffff: "<= distance" passes
                         }
                         u64 key[8];
                         unsigned mask = 0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            key[j] = sj[j] < Ns ? make_key(acc[qi][j], sj[j]) : KEY_MAX;
+                            key[j] = sj[j] < Ns ? make_key(acc[0][j], sj[j]) : KEY_MAX;
                             mask |= (key[j] < tau ? 1u : 0u) << j;
-                            acc[qi][j] = 0.f;
                         }
                         const int c = __popc(mask);
                         int incl = c;
