@@ -64,7 +64,7 @@ constexpr int SMALL_NS = 128;  // source sets up to this size take the k_knn_sma
 
 struct Plan {
     int n_src[LS_MAX_LAYERS], n_dst[LS_MAX_LAYERS];
-    float *xn, *centroid, *s0, *featA, *featB, *dstf, *pooled, *raw, *psrc, *pdst, *bias;
+    float *xn, *centroid, *s0, *featA, *featB, *dstf, *pooled, *raw, *psrc, *pdst, *bias, *gmean;
     int64_t* small_idx;
     int* sel[LS_MAX_LAYERS];
     size_t bytes;
@@ -135,6 +135,7 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
     p.psrc = c.take<float>((size_t)B * std::max<size_t>(psrc, 1));
     p.pdst = c.take<float>((size_t)B * std::max<size_t>(pdst, 1));
     p.bias = c.take<float>((size_t)B * std::max<size_t>(bias, 1));
+    p.gmean = c.take<float>((size_t)B * std::max<size_t>(bias, 1));
     p.small_idx = c.take<int64_t>((size_t)B * std::max<size_t>(small, 1));
     for (int i = 0; i < d->num_layers; ++i)
         p.sel[i] = d->layers[i].down_factor > 1 ? c.take<int>((size_t)B * p.n_dst[i]) : nullptr;
@@ -386,8 +387,10 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         }
         if (L.global_conv) {
             ProfScope ps(5, i, st);
-            k_mean_bias<<<B, 256, (size_t)Co * 3 * sizeof(float), st>>>(p.pooled, Co, Nd, L.w_g2, p.bias);
-            LS_CHECK_LAUNCH("k_mean_bias");
+            k_row_mean<<<dim3((Co * 3 + 7) / 8, B), 256, 0, st>>>(p.pooled, Co * 3, Nd, p.gmean);
+            LS_CHECK_LAUNCH("k_row_mean");
+            k_bias_gemv<<<dim3((2 * Co + 7) / 8, B), 256, (size_t)Co * 3 * sizeof(float), st>>>(p.gmean, Co, L.w_g2, p.bias);
+            LS_CHECK_LAUNCH("k_bias_gemv");
             GemmArgs g{};
             g.W = L.w_g1;
             g.Wtc = L.w_g1_tc;

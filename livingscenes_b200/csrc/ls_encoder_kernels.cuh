@@ -900,37 +900,51 @@ __global__ void __launch_bounds__(256) k_knn_small(const float* __restrict__ src
 
 // ============================================================================================
 // Global context (vec_dgcnn_atten.py:222-225): g = mean_n f ; bias[r][a] = sum_c Wg2[r][c] g[c][a]
-// so that VecLNA_G([f ; g]) = Wg1 f + bias.  One CTA per instance.
+// so that VecLNA_G([f ; g]) = Wg1 f + bias.  Two small kernels, one warp per output element row.
 // ============================================================================================
-__global__ void __launch_bounds__(256) k_mean_bias(const float* __restrict__ f, int Co, int Nd,
-                                                   const float* __restrict__ wg2, float* __restrict__ bias) {
-    extern __shared__ float sg[];  // [Co*3]
-    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const float* fb = f + (size_t)b * Co * 3 * Nd;
-    for (int r = w; r < Co * 3; r += 8) {
-        float s = 0.f;
-        for (int n = lane; n < Nd; n += 32) s += fb[(size_t)r * Nd + n];
-        s = warp_sum(s);
-        if (lane == 0) sg[r] = s / (float)Nd;
+// g[b][r] = mean_n f[b][r][n], r over Co*3 rows
+__global__ void __launch_bounds__(256) k_row_mean(const float* __restrict__ f, int rows, int Nd, float* __restrict__ g) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y, r = blockIdx.x * 8 + w;
+    if (r >= rows) return;
+    const float* p = f + ((size_t)b * rows + r) * Nd;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int n = lane;
+    for (; n + 96 < Nd; n += 128) {
+        s0 += p[n];
+        s1 += p[n + 32];
+        s2 += p[n + 64];
+        s3 += p[n + 96];
     }
+    for (; n < Nd; n += 32) s0 += p[n];
+    const float s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) g[(size_t)b * rows + r] = s / (float)Nd;
+}
+// bias[b][r][a] = sum_c Wg2[r][c] * g[b][c][a]
+__global__ void __launch_bounds__(256) k_bias_gemv(const float* __restrict__ g, int Co, const float* __restrict__ wg2,
+                                                   float* __restrict__ bias) {
+    extern __shared__ float sg[];  // [Co*3]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < Co * 3; i += blockDim.x) sg[i] = g[(size_t)b * Co * 3 + i];
     __syncthreads();
-    for (int r = w; r < 2 * Co; r += 8) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c = lane; c < Co; c += 32) {
-            float wv = __ldg(wg2 + (size_t)r * Co + c);
-            s0 = fmaf(wv, sg[c * 3 + 0], s0);
-            s1 = fmaf(wv, sg[c * 3 + 1], s1);
-            s2 = fmaf(wv, sg[c * 3 + 2], s2);
-        }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-            float* o = bias + ((size_t)b * 2 * Co + r) * 3;
-            o[0] = s0;
-            o[1] = s1;
-            o[2] = s2;
-        }
+    const int r = blockIdx.x * 8 + w;
+    if (r >= 2 * Co) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < Co; c += 32) {
+        const float wv = __ldg(wg2 + (size_t)r * Co + c);
+        s0 = fmaf(wv, sg[c * 3 + 0], s0);
+        s1 = fmaf(wv, sg[c * 3 + 1], s1);
+        s2 = fmaf(wv, sg[c * 3 + 2], s2);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        float* o = bias + ((size_t)b * 2 * Co + r) * 3;
+        o[0] = s0;
+        o[1] = s1;
+        o[2] = s2;
     }
 }
 

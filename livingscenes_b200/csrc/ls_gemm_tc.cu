@@ -238,20 +238,35 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
+        if (PM) {
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const long long base = sh.col_base[cc + j];
-                if (base < 0) continue;
-                float val = __uint_as_float(v[j]);
-                if (PM) {
-                    a.out[base + row_off] = val;  // lanes = consecutive channels: 128 B coalesced
-                } else {
-                    if (a.bias) val += __ldg(a.bias + sh.col_bias[cc + j] + (long long)r * a.bias_sr);
-                    if (a.relu) val = fmaxf(val, 0.f);
-                    a.out[base + (long long)r * a.o_sr] = val;
+                for (int j = 0; j < 32; ++j) {
+                    const long long base = sh.col_base[cc + j];
+                    if (base >= 0) a.out[base + row_off] = __uint_as_float(v[j]);  // lanes = consecutive channels
                 }
             }
+        } else {
+            // channel-major: transpose the warp's 32 rows x 32 columns through shared memory (the operand
+            // stages are free once bar_done has fired) so that lanes store consecutive columns of one row
+            float* tile = &sh.a[0][0][0] + w * (32 * 33);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const long long base = sh.col_base[cc + lane];
+            const long long bo = sh.col_bias[cc + lane];
+            if (base >= 0) {
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int row = r0 + w * 32 + rr;
+                    if (row >= a.R) break;
+                    float val = tile[rr * 33 + lane];
+                    if (a.bias) val += __ldg(a.bias + bo + (long long)row * a.bias_sr);
+                    if (a.relu) val = fmaxf(val, 0.f);
+                    a.out[base + (long long)row * a.o_sr] = val;
+                }
+            }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
