@@ -94,7 +94,10 @@ __device__ __forceinline__ void vn_act(float q0, float q1, float q2, float k0, f
                                        float one_minus_slope, float& o0, float& o1, float& o2) {
     float n2 = fmaf(k2, k2, fmaf(k1, k1, k0 * k0));
     float dt = fmaf(q2, k2, fmaf(q1, k1, q0 * k0));
-    float t = one_minus_slope * fminf(dt, 0.f) / fmaxf(n2, EPS_NRM2);
+    // num * rcp(den) instead of num / den: the numerator is exactly 0 whenever <q,k> >= 0, which sends the
+    // IEEE division through its slow path (exponent check on the NUMERATOR) for practically every warp --
+    // 14 % of the layer-2 kernel in the round-1 profile.  den >= 1e-24 is always a normal number.
+    float t = (one_minus_slope * fminf(dt, 0.f)) * __frcp_rn(fmaxf(n2, EPS_NRM2));
     o0 = fmaf(-t, k0, q0);
     o1 = fmaf(-t, k1, q1);
     o2 = fmaf(-t, k2, q2);
