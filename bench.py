@@ -270,13 +270,37 @@ def run_b200(args):
         step(dev_sets[w % N_INPUT_SETS])
     barrier()
 
+    # ---- capture the whole step (encode -> [all-gather] -> match -> pose: ~75 launches) in ONE CUDA graph.
+    # Every C-ABI call launches on torch's current stream, takes caller-owned workspaces and never
+    # synchronises, so the step is capturable as is; the input lives in a static buffer that is refilled
+    # (device copy for `value`, H2D copy for `e2e`) before each replay.  NCCL all-gather is captured too.
+    use_graph = not args.no_graph
+    x_static = dev_sets[0].clone()
+    graph, static_out = None, None
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                step(x_static)
+        torch.cuda.current_stream().wait_stream(side)
+        barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = step(x_static)
+        barrier()
+
+    def run_step(x_src, non_blocking=False):
+        if graph is None:
+            return step(x_src if x_src.is_cuda else x_src.to(dev, non_blocking=non_blocking))
+        x_static.copy_(x_src, non_blocking=non_blocking)
+        graph.replay()
+        return static_out
+
     # ---------------- timed region 1: inputs resident in HBM
-    _lib.profile_enable(True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    stage_ms = {}
-    launches0 = _lib.kernel_launches()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
@@ -284,17 +308,33 @@ def run_b200(args):
     for k in range(args.steps):
         flush.zero_()                                   # evict L2 between timed steps (not timed)
         ev[k][0].record()
-        out = step(dev_sets[k % N_INPUT_SETS])
+        out = run_step(dev_sets[k % N_INPUT_SETS])
         ev[k][1].record()
         ev[k][1].synchronize()
         total_ms += ev[k][0].elapsed_time(ev[k][1])
-        for name, layer, ms in _lib.profile_read():
-            stage_ms.setdefault((name, layer), []).append(ms)
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- the same K steps launched eagerly with per-stage CUDA events (ls_profile_*): kernel
+    # durations for the roofline, and the launch count of one step (a graph replay issues the same kernels)
+    _lib.profile_enable(True)
+    stage_ms = {}
+    launches0 = _lib.kernel_launches()
+    eager_ms = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        step(dev_sets[k % N_INPUT_SETS])
+        b_.record()
+        b_.synchronize()
+        eager_ms += a_.elapsed_time(b_)
+        for name, layer, ms in _lib.profile_read():
+            stage_ms.setdefault((name, layer), []).append(ms)
     launches = _lib.kernel_launches() - launches0
     _lib.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
+    barrier()
 
     # ---------------- timed region 2: end to end from pinned host memory
     h_m = torch.empty(PAIRS_PER_GPU * INST_PER_SET, dtype=torch.int64).pin_memory()
@@ -306,8 +346,7 @@ def run_b200(args):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        x = host_sets[k % N_INPUT_SETS].to(dev, non_blocking=True)
-        m0, R, t, _ = step(x)
+        m0, R, t, _ = run_step(host_sets[k % N_INPUT_SETS], non_blocking=True)
         h_m.copy_(m0, non_blocking=True)
         h_R.copy_(R, non_blocking=True)
         h_t.copy_(t, non_blocking=True)
@@ -373,7 +412,8 @@ def run_b200(args):
                        "instances_per_gpu": INST_PER_GPU, "n_points": N_POINTS, "pairs_per_gpu": PAIRS_PER_GPU,
                        "parallelism": f"instance-sharded x{world}" + (" + 1 NCCL all-gather of packed codes" if world > 1 else ""),
                        "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set ~2 GB >> 126 MB L2",
-                       "timing": "CUDA events per step on the launching stream, summed over K steps, max over ranks"},
+                       "timing": "CUDA events per step on the launching stream, summed over K steps, max over ranks",
+                       "launch": "one CUDA graph replay per step" if graph is not None else "eager launches"},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
@@ -388,6 +428,7 @@ def run_b200(args):
                          "all_layers": all_layers},
             "cpu_baseline": cpu,
             "stages_ms": stages,
+            "eager_ms_per_step": eager_ms / args.steps,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
         }
         print(json.dumps(line))
@@ -403,6 +444,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
