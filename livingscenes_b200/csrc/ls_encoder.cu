@@ -90,8 +90,7 @@ int check_desc(const ls_encoder_desc* d, int N) {
             int cpl = L.c_out / 32;
             LS_REQUIRE(cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8 || cpl == 16, "c_out/32 must be a power of two <= 16");
         }
-        LS_REQUIRE(n % L.down_factor == 0, "N must be divisible by the down-sampling factors");
-        n /= L.down_factor;
+        n /= L.down_factor;  // floor, like N_ori // factor in vec_dgcnn_atten.py:166
         LS_REQUIRE(n >= LS_KNN_K, "too few points for K=16 neighbours at a deep layer (N too small)");
     }
     LS_REQUIRE(d->w_conv_c && d->w_inv_t, "missing head weights");

@@ -447,8 +447,8 @@ int run_match(const float* z0, const float* z1, int dim, const int32_t* off0, co
         ws_off = ws_end;
         const int threads = max_nm <= 4096 ? 256 : 1024;
         if (SEQ) {
-            k_seq_match<<<count, threads, (size_t)max_npm + 16, st>>>(z0, z1, dim, tab, static_cast<float*>(ws), m0, m1);
-            LS_CHECK_LAUNCH("k_seq_match");
+                k_seq_match<<<count, threads, (size_t)max_npm + 16, st>>>(z0, z1, dim, tab, static_cast<float*>(ws), m0, m1);
+                LS_CHECK_LAUNCH("k_seq_match");
         } else {
             const size_t smem = (size_t)max_npm * sizeof(int) + 16;
             if (smem > 48 * 1024)
