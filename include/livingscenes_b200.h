@@ -135,7 +135,7 @@ LS_API int ls_encoder_forward(const ls_encoder_desc* desc, const ls_encoder_io* 
  * stage with CUDA events on the launching stream; after the caller has synchronised the stream,
  * ls_profile_read returns (stage, layer, milliseconds) of the LAST forward call.
  * stage: 0 normalize, 1 fps, 2 gather dst, 3 point-level GEMM tables, 4 fused kNN+EdgeConv+pool,
- *        5 global-context conv, 6 head.  ls_kernel_launches counts every kernel this library launched. */
+ *        5 global-context conv, 6 head, 7 tensor-core kNN filter (pack + filter).  ls_kernel_launches counts every kernel this library launched. */
 LS_API int ls_profile_enable(int32_t on);
 LS_API int ls_profile_read(int32_t* stage, int32_t* layer, float* ms, int32_t max_entries, int32_t* n_entries);
 LS_API int64_t ls_kernel_launches(void);
@@ -150,6 +150,10 @@ LS_API int ls_tc_packed_floats(int32_t R, int32_t K, size_t* n_floats);
 LS_API int ls_tc_pack_weights(const float* W, int32_t R, int32_t K, int32_t ldw, float* packed, void* stream);
 LS_API int ls_vn_linear(const float* W, const float* packed, const float* X, float* out, int32_t R, int32_t K,
                         int32_t ldw, int32_t B, int32_t n, void* stream);
+/* kNN graph: 1 (default) = tcgen05 3xTF32 candidate filter + exact fp32 re-rank, 0 = exact fp32 brute force.
+ * Both produce the same indices; kappa_scale (> 0, default 1) scales the filter's error budget (tests use a
+ * huge value to force the candidate-overflow fallback). */
+LS_API int ls_set_knn_tensor_cores(int32_t on, float kappa_scale);
 LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 path where packed weights exist */
 
 /* ------------------------------------------------------------------------------------------

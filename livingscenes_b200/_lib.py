@@ -79,6 +79,7 @@ _PROTOS = {
     "ls_vn_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p]),
     "ls_set_tensor_cores": (C.c_int, [C.c_int32]),
+    "ls_set_knn_tensor_cores": (C.c_int, [C.c_int32, C.c_float]),
     "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_fps": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_match_workspace_bytes": (C.c_int, [c_i32_p, c_i32_p, C.c_int32, C.POINTER(C.c_size_t)]),
@@ -143,7 +144,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
             "(the CPU restatement lives in oracle/ and is test infrastructure only).")
 
 
-STAGE_NAMES = ("normalize", "fps", "gather", "gemm_tables", "knn_edgeconv", "global_conv", "head")
+STAGE_NAMES = ("normalize", "fps", "gather", "gemm_tables", "knn_edgeconv", "global_conv", "head", "knn_filter")
 
 
 def profile_enable(on: bool) -> None:
@@ -165,6 +166,11 @@ def kernel_launches() -> int:
 def set_tensor_cores(on: bool) -> None:
     """Route the packed-weight GEMMs through the tcgen05 3xTF32 kernel (default) or the FP32 SIMT kernel."""
     check(lib().ls_set_tensor_cores(int(on)), "ls_set_tensor_cores")
+
+
+def set_knn_tensor_cores(on: bool, kappa_scale: float = 1.0) -> None:
+    """kNN graph through the tcgen05 candidate filter + exact re-rank (default) or the exact brute-force tiles."""
+    check(lib().ls_set_knn_tensor_cores(int(on), float(kappa_scale)), "ls_set_knn_tensor_cores")
 
 
 def tc_pack(weight_dev: torch.Tensor) -> torch.Tensor:

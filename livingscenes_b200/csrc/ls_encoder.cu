@@ -61,11 +61,17 @@ struct Carver {
 };
 
 constexpr int SMALL_NS = 128;  // source sets up to this size take the k_knn_small path
+bool g_use_knn_tc = true;      // tensor-core candidate filter for the larger source sets
+float g_knn_tc_kappa_scale = 1.f;
 
 struct Plan {
     int n_src[LS_MAX_LAYERS], n_dst[LS_MAX_LAYERS];
     float *xn, *centroid, *s0, *featA, *featB, *dstf, *pooled, *raw, *psrc, *pdst, *bias, *gmean;
     int64_t* small_idx;
+    // tensor-core kNN filter (ls_knn_tc.cu): packed images / norms / point-major copies and candidate lists
+    float *kimg_s, *knrm_s, *kpm_s, *kimg_q, *knrm_q, *kpm_q;
+    unsigned short* kcand;
+    int* kcnt;
     int* sel[LS_MAX_LAYERS];
     size_t bytes;
 };
@@ -101,6 +107,7 @@ int check_desc(const ls_encoder_desc* d, int N) {
 void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
     Carver c(ws);
     size_t feat = 0, dstf = 0, pooled = 0, raw = 0, psrc = 0, pdst = 0, bias = 0, small = 0;
+    size_t kimg_s = 0, knrm_s = 0, kpm_s = 0, kimg_q = 0, knrm_q = 0, kpm_q = 0, kcand = 0;
     int n = N;
     for (int i = 0; i < d->num_layers; ++i) {
         const ls_enc_layer_desc& L = d->layers[i];
@@ -108,7 +115,20 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
         n /= L.down_factor;
         p.n_dst[i] = n;
         const size_t co = L.c_out, ci = L.c_in;
-        if (p.n_src[i] <= SMALL_NS) small = std::max(small, (size_t)n * LS_KNN_K);
+        if (p.n_src[i] <= SMALL_NS) {
+            small = std::max(small, (size_t)n * LS_KNN_K);
+        } else {
+            const int D = (int)ci * 3;
+            kimg_s = std::max(kimg_s, knn_tc_img_floats(p.n_src[i], D));
+            knrm_s = std::max(knrm_s, knn_tc_nrm_floats(p.n_src[i]));
+            kpm_s = std::max(kpm_s, knn_tc_pm_floats(p.n_src[i], D));
+            if (L.down_factor > 1) {
+                kimg_q = std::max(kimg_q, knn_tc_img_floats(n, D));
+                knrm_q = std::max(knrm_q, knn_tc_nrm_floats(n));
+                kpm_q = std::max(kpm_q, knn_tc_pm_floats(n, D));
+            }
+            kcand = std::max(kcand, knn_tc_cand_u16(n));
+        }
         feat = std::max(feat, co * 3 * (size_t)n);
         if (L.down_factor > 1) dstf = std::max(dstf, ci * 3 * (size_t)n);
         if (L.global_conv) {
@@ -136,6 +156,14 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
     p.bias = c.take<float>((size_t)B * std::max<size_t>(bias, 1));
     p.gmean = c.take<float>((size_t)B * std::max<size_t>(bias, 1));
     p.small_idx = c.take<int64_t>((size_t)B * std::max<size_t>(small, 1));
+    p.kimg_s = c.take<float>((size_t)B * std::max<size_t>(kimg_s, 1));
+    p.knrm_s = c.take<float>((size_t)B * std::max<size_t>(knrm_s, 1));
+    p.kpm_s = c.take<float>((size_t)B * std::max<size_t>(kpm_s, 1));
+    p.kimg_q = c.take<float>((size_t)B * std::max<size_t>(kimg_q, 1));
+    p.knrm_q = c.take<float>((size_t)B * std::max<size_t>(knrm_q, 1));
+    p.kpm_q = c.take<float>((size_t)B * std::max<size_t>(kpm_q, 1));
+    p.kcand = c.take<unsigned short>((size_t)B * std::max<size_t>(kcand, 1));
+    p.kcnt = c.take<int>((size_t)B * std::max<size_t>(knrm_s + knrm_q, 1));
     for (int i = 0; i < d->num_layers; ++i)
         p.sel[i] = d->layers[i].down_factor > 1 ? c.take<int>((size_t)B * p.n_dst[i]) : nullptr;
     p.bytes = (c.off + 255) & ~size_t(255);
@@ -335,7 +363,41 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             LS_CHECK_LAUNCH("k_knn_small");
             ea.idx_in = p.small_idx;
         }
-        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr);
+        if (ea.idx_in == nullptr && g_use_knn_tc) {
+            // tensor-core candidate filter + exact re-rank instead of the brute-force phase 1
+            ProfScope ps(7, i, st);
+            const int D = Ci * 3;
+            rc = launch_knn_pack(src_f, B, D, Ns, p.kimg_s, p.knrm_s, p.kpm_s, st);
+            if (rc != LS_OK) return rc;
+            KnnTcArgs ka{};
+            ka.img_s = p.kimg_s;
+            ka.nrm_s = p.knrm_s;
+            ka.img_q = p.kimg_s;
+            ka.nrm_q = p.knrm_s;
+            ea.pm_s = p.kpm_s;
+            ea.pm_q = p.kpm_s;
+            if (L.down_factor > 1) {
+                rc = launch_knn_pack(dst_f, B, D, Nd, p.kimg_q, p.knrm_q, p.kpm_q, st);
+                if (rc != LS_OK) return rc;
+                ka.img_q = p.kimg_q;
+                ka.nrm_q = p.knrm_q;
+                ea.pm_q = p.kpm_q;
+            }
+            ka.Ns = Ns;
+            ka.Nd = Nd;
+            ka.n_pt_s = knn_tc_tiles(Ns);
+            ka.n_pt_q = knn_tc_tiles(Nd);
+            ka.n_kb = knn_tc_kblocks(D);
+            ka.kappa = g_knn_tc_kappa_scale * knn_tc_kappa(D);
+            ka.cand = p.kcand;
+            ka.cnt = p.kcnt;
+            rc = launch_knn_tc(ka, B, st);
+            if (rc != LS_OK) return rc;
+            ea.cand = p.kcand;
+            ea.cand_cnt = p.kcnt;
+            ea.Dp = ka.n_kb * KT_KB;
+        }
+        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr || ea.cand != nullptr);
         if (i == 0) {
             ea.w0 = L.w0;
             ProfScope ps(4, i, st);
@@ -479,6 +541,11 @@ int ls_tc_packed_floats(int32_t R, int32_t K, size_t* n_floats) {
 }
 int ls_tc_pack_weights(const float* W, int32_t R, int32_t K, int32_t ldw, float* packed, void* stream) {
     return tc_pack_weights(W, R, K, ldw, packed, static_cast<cudaStream_t>(stream));
+}
+int ls_set_knn_tensor_cores(int32_t on, float kappa_scale) {
+    ls::g_use_knn_tc = on != 0;
+    ls::g_knn_tc_kappa_scale = kappa_scale > 0.f ? kappa_scale : 1.f;
+    return LS_OK;
 }
 int ls_set_tensor_cores(int32_t on) {
     ls::g_use_tensor_cores = on != 0;

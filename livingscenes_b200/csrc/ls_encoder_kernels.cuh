@@ -4,6 +4,7 @@
 #include <float.h>
 
 #include "ls_common.cuh"
+#include "ls_knn_tc.cuh"
 
 namespace ls {
 
@@ -299,6 +300,12 @@ struct EdgeArgs {
     int64_t* idx_out;        // optional [B][Nd][16]
     const int64_t* idx_in;   // optional: graph given (teacher forcing, or built by k_knn_small)
     float* dist_out;         // optional [B][Nd][16] (MODE_KNN_ONLY)
+    // candidate lists of the tensor-core filter (ls_knn_tc.cu): exact re-rank replaces the brute-force phase 1
+    const unsigned short* cand;  // optional [B][ceil(Nd/128)][KT_CAP][128]
+    const int* cand_cnt;         // [B][ceil(Nd/128)*128], -1 = overflow -> brute force that query
+    const float* pm_s;           // [B][Ns][Dp] point-major fp32 features of the sources
+    const float* pm_q;           // [B][Nd][Dp] ... of the queries
+    int Dp;
 };
 
 // ---- warp-level top-k machinery.  A candidate is ONE 64-bit key: (float bits of the squared distance
@@ -403,6 +410,69 @@ __device__ __noinline__ SelRet knn_select_slow(u64 k0, u64 k1, u64 k2, u64 k3, u
     return SelRet{lk, cnt};
 }
 
+// ---- exact re-rank of the tensor-core candidates.  The squared distance is the reference's direct form
+//      sum_d (q_d - s_d)^2 accumulated with one fp32 FMA per dimension in ascending d -- the same operation
+//      sequence as the brute-force tiles above, so both paths produce bit-identical keys.
+__device__ __forceinline__ float exact_dist_pm(const float* __restrict__ qrow, const float* __restrict__ srow, int Dp) {
+    float acc = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < Dp; d += 4) {
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow + d));
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + d));
+        float df = __fsub_rn(qv.x, sv.x);
+        acc = __fmaf_rn(df, df, acc);
+        df = __fsub_rn(qv.y, sv.y);
+        acc = __fmaf_rn(df, df, acc);
+        df = __fsub_rn(qv.z, sv.z);
+        acc = __fmaf_rn(df, df, acc);
+        df = __fsub_rn(qv.w, sv.w);
+        acc = __fmaf_rn(df, df, acc);
+    }
+    return acc;
+}
+// one warp, one query: lanes = candidates (32 per round); returns the sorted list element of this lane
+__device__ __noinline__ u64 knn_rerank(const float* qrow, const float* pms, const unsigned short* cl, int cnt, int Dp) {
+    const int lane = threadIdx.x & 31;
+    u64 lk = KEY_MAX;
+    for (int r0 = 0; r0 < cnt; r0 += 32) {
+        const int slot = r0 + lane;
+        u64 key = KEY_MAX;
+        if (slot < cnt) {
+            const int s = (int)__ldg(cl + (size_t)slot * KT_PTS);
+            key = make_key(exact_dist_pm(qrow, pms + (size_t)s * Dp, Dp), s);
+        }
+        __syncwarp();
+        if (r0 == 0) {
+            bitonic_sort32(key, lane, false);
+            lk = key;
+        } else {
+            bitonic_sort32(key, lane, true);
+            lk = key < lk ? key : lk;
+            bitonic_merge32(lk, lane);
+        }
+    }
+    return lk;
+}
+// exact brute force of one query over all sources (candidate-list overflow; never taken on sane inputs)
+__device__ __noinline__ u64 knn_bruteforce_pm(const float* qrow, const float* pms, int Ns, int Dp) {
+    const int lane = threadIdx.x & 31;
+    u64 lk = KEY_MAX;
+    for (int s0 = 0; s0 < Ns; s0 += 32) {
+        const int s = s0 + lane;
+        u64 key = s < Ns ? make_key(exact_dist_pm(qrow, pms + (size_t)s * Dp, Dp), s) : KEY_MAX;
+        __syncwarp();
+        if (s0 == 0) {
+            bitonic_sort32(key, lane, false);
+            lk = key;
+        } else {
+            bitonic_sort32(key, lane, true);
+            lk = key < lk ? key : lk;
+            bitonic_merge32(lk, lane);
+        }
+    }
+    return lk;
+}
+
 template <int MODE, int CPL>
 __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) {
     // phase-1 tiles and phase-2 scratch share one buffer
@@ -425,6 +495,22 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
         for (int e = t; e < nq * LS_KNN_K; e += EDGE_THREADS) {
             int ql = e >> 4, k = e & 15;
             sIdx[ql][k] = (int)a.idx_in[((size_t)b * Nd + q0 + ql) * LS_KNN_K + k];
+        }
+    } else if (a.cand != nullptr) {
+        // ------------------------------------------------------------------ phase 1': exact re-rank
+        const int n_pt_q = (Nd + KT_PTS - 1) / KT_PTS;
+        const int qtile = q0 / KT_PTS, tq0 = q0 % KT_PTS;  // qpc divides 128: a CTA never straddles a tile
+        const unsigned short* cl = a.cand + ((size_t)b * n_pt_q + qtile) * KT_CAP * KT_PTS + tq0;
+        const int* cc = a.cand_cnt + ((size_t)b * n_pt_q + qtile) * KT_PTS + tq0;
+        const float* pms = a.pm_s + (size_t)b * Ns * a.Dp;
+        for (int ql = w; ql < nq; ql += EDGE_THREADS / 32) {
+            const float* qrow = a.pm_q + ((size_t)b * Nd + q0 + ql) * a.Dp;
+            const int c = __ldg(cc + ql);
+            const u64 lk = c < 0 ? knn_bruteforce_pm(qrow, pms, Ns, a.Dp) : knn_rerank(qrow, pms, cl + ql, c, a.Dp);
+            if (lane < LS_KNN_K) {
+                sIdx[ql][lane] = min(key_idx(lk) & 0x7fffffff, Ns - 1);
+                if (MODE == MODE_KNN_ONLY) sDist[ql][lane] = key_dist(lk);
+            }
         }
     } else {
         // ------------------------------------------------------------------ phase 1: kNN

@@ -1,0 +1,377 @@
+// Tensor-core candidate filter for the feature-space kNN graph (get_graph_feature + pytorch3d knn_points,
+// vec_dgcnn_atten.py:124-147) -- the part of the fused kNN+EdgeConv path that was FP32-issue bound.
+//
+// The reference ranks sources by the fp32 direct form  d(q,s) = sum_k (q_k - s_k)^2.  Brute force costs
+// Nd*Ns*D FMAs.  Here the tensor cores compute a ranking value that is provably close to d,
+//
+//     dt(q,s) = |s|^2 - 2 <q,s>        (= d - |q|^2 up to rounding;  <q,s> as a 3xTF32 tcgen05 product)
+//
+// and only a short candidate list per query is re-ranked exactly (k_knn_edge, ls_encoder_kernels.cuh):
+//
+//   * tau  = 16th smallest of 32 group minima of dt (group = source index mod 32): at least 16 sources have
+//            dt <= tau, so tau >= T := the true 16th smallest dt;
+//   * E    = kappa * (|q|^2 + max_s |s|^2) bounds |dt + |q|^2 - d_fp32| (tensor-core rounding of the product,
+//            fp32 rounding of the norms and of the direct form itself; kappa = 2 D 2^-23 + 2^-16 is ~40x the
+//            error measured for this product);
+//   * 16 sources have d <= T + |q|^2 + E, hence every member of the exact top-16 has dt <= T + 2E <= tau + 2E:
+//            the candidate set {dt <= tau + 2E} CONTAINS the exact answer; ~22 candidates per query on the
+//            shipped model (scripts/emulate_tc_knn.py), the exact re-rank then decides order and ties.
+//   * a query whose list overflows is flagged (count -1) and brute-forced exactly by the consumer.
+//
+// k_knn_pack   features [B][D][N] -> per (128-point tile, 8-dim k-block) the canonical UMMA shared-memory
+//              image (K-major, no swizzle, [kcore 2][row group 16][8 rows][4 k]) of hi = RN_tf32(x) and
+//              lo = x - hi, the squared norms, and a point-major fp32 copy [B][N][Dp] for the exact re-rank.
+// k_knn_tc     one CTA = 128 queries (TMEM lanes) x all sources of one instance, 512 sources (= all 512 TMEM
+//              columns, 4 MMA tiles of N=128) per group.  Warp 4: one thread streams 8 KB image blocks with
+//              cp.async.bulk (mbarrier complete_tx, 3-stage ring) and issues tcgen05.mma kind::tf32
+//              (lo*hi + hi*lo + hi*hi).  Warps 0-3: thread = query; per group one tcgen05.ld sweep for the
+//              group minima, one for the threshold filter into a shared-memory stash, final filter with
+//              the tightest threshold into the global candidate list.
+#include <float.h>
+
+#include "ls_common.cuh"
+#include "ls_knn_tc.cuh"
+
+namespace ls {
+namespace {
+
+constexpr int KT_IMG = KT_PTS * KT_KB;  // floats per hi (or lo) image of one block
+constexpr int KT_BLOCK = 2 * KT_IMG;    // hi + lo: 2048 floats = 8 KB
+constexpr int KT_GT = 4;                // source tiles per group (4 x 128 = 512 TMEM columns)
+constexpr int KT_STAGES = 3;
+constexpr int KT_STASH = 80;            // shared-memory stash slots per query
+constexpr int KT_THREADS = 160;
+constexpr int KT_TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "KT_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra KT_DONE;\n\t"
+        "bra KT_WAIT;\n\t"
+        "KT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// smem matrix descriptor, no swizzle: start address, leading (k-core) / stride (row-group) byte offsets >> 4
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// D = f32, A = B = tf32, both K-major, N = 128, M = 128 (same encoding as ls_gemm_tc.cu)
+constexpr uint32_t KT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((KT_PTS >> 3) << 17) | ((KT_PTS >> 4) << 24);
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(KT_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------- pack
+__global__ void __launch_bounds__(KT_PTS) k_knn_pack(const float* __restrict__ f, int D, int N, int n_pt, int n_kb,
+                                                     float* __restrict__ img, float* __restrict__ nrm,
+                                                     float* __restrict__ pm) {
+    const int b = blockIdx.y, pt = blockIdx.x, t = threadIdx.x;
+    const int p = pt * KT_PTS + t;
+    const bool ok = p < N;
+    const float* fb = f + (size_t)b * D * N;
+    float* tile = img + ((size_t)b * n_pt + pt) * n_kb * KT_BLOCK;
+    const int Dp = n_kb * KT_KB;
+    float nr = 0.f;
+    for (int kb = 0; kb < n_kb; ++kb) {
+        float x[KT_KB], h[KT_KB], l[KT_KB];
+#pragma unroll
+        for (int j = 0; j < KT_KB; ++j) {
+            const int d = kb * KT_KB + j;
+            x[j] = (ok && d < D) ? __ldg(fb + (size_t)d * N + p) : 0.f;
+            nr = fmaf(x[j], x[j], nr);
+            // hi = x rounded to the nearest TF32 number (ties away), lo = x - hi exactly
+            h[j] = __uint_as_float((__float_as_uint(x[j]) + 0x1000u) & 0xffffe000u);
+            l[j] = x[j] - h[j];
+        }
+        float* dst = tile + (size_t)kb * KT_BLOCK;
+        // image float offset = kcore*512 + row*4 + k: consecutive threads write consecutive 16-byte rows
+        *reinterpret_cast<float4*>(dst + t * 4) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dst + 512 + t * 4) = make_float4(h[4], h[5], h[6], h[7]);
+        *reinterpret_cast<float4*>(dst + KT_IMG + t * 4) = make_float4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<float4*>(dst + KT_IMG + 512 + t * 4) = make_float4(l[4], l[5], l[6], l[7]);
+        if (ok) {
+            float* row = pm + ((size_t)b * N + p) * Dp + kb * KT_KB;
+            *reinterpret_cast<float4*>(row) = make_float4(x[0], x[1], x[2], x[3]);
+            *reinterpret_cast<float4*>(row + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        }
+    }
+    nrm[((size_t)b * n_pt + pt) * KT_PTS + t] = ok ? nr : __int_as_float(0x7f800000);
+}
+
+// ------------------------------------------------------------------------------------------- filter
+struct KtShared {
+    float stage[KT_STAGES][1 + KT_GT][KT_BLOCK];  // [stage][0 = query tile, 1.. = source tiles][hi | lo]
+    float ns[2][KT_GT * KT_PTS];                  // squared norms of the current group's sources
+    float stash_d[KT_STASH][KT_PTS];
+    unsigned short stash_i[KT_STASH][KT_PTS];
+    float red[4];
+    uint64_t full[KT_STAGES], empty[KT_STAGES], tmem_full, tmem_empty;
+    uint32_t tmem_base;
+};
+
+// 16th smallest of 32 per-thread values (bitonic network on registers, fully unrolled)
+__device__ __forceinline__ float kth16_of_32(const float* m) {
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = m[i];
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const float lo = fminf(a[i], a[l]), hi = fmaxf(a[i], a[l]);
+                    a[i] = up ? lo : hi;
+                    a[l] = up ? hi : lo;
+                }
+            }
+        }
+    }
+    return a[15];
+}
+
+__global__ void __launch_bounds__(KT_THREADS, 1) k_knn_tc(const KnnTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KtShared& sh = *reinterpret_cast<KtShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int b = blockIdx.y, qt = blockIdx.x;
+    const int n_groups = (a.n_pt_s + KT_GT - 1) / KT_GT;
+    const int n_kb = a.n_kb;
+
+    if (t == 0) {
+        for (int s = 0; s < KT_STAGES; ++s) {
+            mbar_init(&sh.full[s], 1);
+            mbar_init(&sh.empty[s], 1);
+        }
+        mbar_init(&sh.tmem_full, 1);
+        mbar_init(&sh.tmem_empty, KT_PTS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 4) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+                     "r"(KT_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sh.tmem_base;
+
+    if (w == 4) {
+        // ================================================================ producer + MMA issuer
+        if (lane == 0) {
+            const float* qimg = a.img_q + ((size_t)b * a.n_pt_q + qt) * n_kb * KT_BLOCK;
+            const float* simg = a.img_s + (size_t)b * a.n_pt_s * n_kb * KT_BLOCK;
+            const int total = n_groups * n_kb;
+            auto load = [&](int it) {
+                const int stage = it % KT_STAGES, g = it / n_kb, kb = it - g * n_kb;
+                const int tiles = min(KT_GT, a.n_pt_s - g * KT_GT);
+                if (it >= KT_STAGES) mbar_wait(&sh.empty[stage], ((it / KT_STAGES) - 1) & 1);
+                mbar_arrive_expect_tx(&sh.full[stage], (uint32_t)((1 + tiles) * KT_BLOCK * sizeof(float)));
+                bulk_g2s(&sh.stage[stage][0][0], qimg + (size_t)kb * KT_BLOCK, KT_BLOCK * sizeof(float), &sh.full[stage]);
+                for (int tl = 0; tl < tiles; ++tl)
+                    bulk_g2s(&sh.stage[stage][1 + tl][0], simg + ((size_t)(g * KT_GT + tl) * n_kb + kb) * KT_BLOCK,
+                             KT_BLOCK * sizeof(float), &sh.full[stage]);
+            };
+            for (int it = 0; it < KT_STAGES - 1 && it < total; ++it) load(it);
+            for (int it = 0; it < total; ++it) {
+                const int stage = it % KT_STAGES, g = it / n_kb, kb = it - g * n_kb;
+                const int tiles = min(KT_GT, a.n_pt_s - g * KT_GT);
+                if (kb == 0 && g > 0) {  // the epilogue must have drained the previous group's accumulators
+                    mbar_wait(&sh.tmem_empty, (g - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                mbar_wait(&sh.full[stage], (it / KT_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t q_hi = smem_u32(&sh.stage[stage][0][0]), q_lo = q_hi + KT_IMG * 4;
+                const uint64_t dqh = make_desc(q_hi, (KT_PTS / 8) * 128, 128), dql = make_desc(q_lo, (KT_PTS / 8) * 128, 128);
+                for (int tl = 0; tl < tiles; ++tl) {
+                    const uint32_t s_hi = smem_u32(&sh.stage[stage][1 + tl][0]), s_lo = s_hi + KT_IMG * 4;
+                    const uint64_t dsh = make_desc(s_hi, (KT_PTS / 8) * 128, 128), dsl = make_desc(s_lo, (KT_PTS / 8) * 128, 128);
+                    const uint32_t d = tmem + (uint32_t)(tl * KT_PTS);
+                    umma_tf32(d, dql, dsh, kb != 0);
+                    umma_tf32(d, dqh, dsl, 1);
+                    umma_tf32(d, dqh, dsh, 1);
+                }
+                umma_commit(&sh.empty[stage]);
+                if (kb == n_kb - 1) umma_commit(&sh.tmem_full);
+                const int nxt = it + KT_STAGES - 1;
+                if (nxt < total) load(nxt);
+            }
+        }
+    } else {
+        // ================================================================ epilogue: thread = query
+        const int q = qt * KT_PTS + t;
+        const bool valid = q < a.Nd;
+        const float inf = __int_as_float(0x7f800000);
+        // max_s |s|^2 of the instance
+        float mx = 0.f;
+        {
+            const float* nsb = a.nrm_s + (size_t)b * a.n_pt_s * KT_PTS;
+            for (int s = t; s < a.Ns; s += KT_PTS) mx = fmaxf(mx, __ldg(nsb + s));
+            mx = warp_max(mx);
+            if (lane == 0) sh.red[w] = mx;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mx = fmaxf(fmaxf(sh.red[0], sh.red[1]), fmaxf(sh.red[2], sh.red[3]));
+        }
+        const float nq = valid ? __ldg(a.nrm_q + ((size_t)b * a.n_pt_q + qt) * KT_PTS + t) : 0.f;
+        const float e2 = 2.f * a.kappa * (nq + mx);
+        float m[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m[j] = inf;
+        int cnt = 0;
+        bool overflow = false;
+        float thr = inf;
+        const uint32_t tlane = tmem + ((uint32_t)(w * 32) << 16);
+
+        for (int g = 0; g < n_groups; ++g) {
+            const int tiles = min(KT_GT, a.n_pt_s - g * KT_GT);
+            const int ncols = tiles * KT_PTS;
+            float* ns = sh.ns[g & 1];
+            {
+                const float* nsg = a.nrm_s + ((size_t)b * a.n_pt_s + g * KT_GT) * KT_PTS;
+                if (t * 4 < ncols) *reinterpret_cast<float4*>(ns + t * 4) = __ldg(reinterpret_cast<const float4*>(nsg + t * 4));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&sh.tmem_full, g & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- sweep 1: group minima (group = column mod 32)
+            for (int c = 0; c < ncols; c += 32) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld32(tlane + (uint32_t)c, v);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 n4 = *reinterpret_cast<const float4*>(ns + c + 4 * j4);
+                    m[4 * j4 + 0] = fminf(m[4 * j4 + 0], fmaf(-2.f, __uint_as_float(v[4 * j4 + 0]), n4.x));
+                    m[4 * j4 + 1] = fminf(m[4 * j4 + 1], fmaf(-2.f, __uint_as_float(v[4 * j4 + 1]), n4.y));
+                    m[4 * j4 + 2] = fminf(m[4 * j4 + 2], fmaf(-2.f, __uint_as_float(v[4 * j4 + 2]), n4.z));
+                    m[4 * j4 + 3] = fminf(m[4 * j4 + 3], fmaf(-2.f, __uint_as_float(v[4 * j4 + 3]), n4.w));
+                }
+            }
+            thr = kth16_of_32(m) + e2;
+            // ---- sweep 2: everything that may still belong to the exact top-16 goes to the stash
+            for (int c = 0; c < ncols; c += 32) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld32(tlane + (uint32_t)c, v);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 n4 = *reinterpret_cast<const float4*>(ns + c + 4 * j4);
+                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float dt = fmaf(-2.f, __uint_as_float(v[4 * j4 + jj]), nn[jj]);
+                        if (dt <= thr && valid) {
+                            if (cnt < KT_STASH) {
+                                sh.stash_d[cnt][t] = dt;
+                                sh.stash_i[cnt][t] = (unsigned short)(g * KT_GT * KT_PTS + c + 4 * j4 + jj);
+                                ++cnt;
+                            } else {
+                                overflow = true;
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&sh.tmem_empty);
+        }
+        // ---- final filter with the tightest threshold -> global candidate list [b][qt][slot][128]
+        if (valid) {
+            unsigned short* cl = a.cand + ((size_t)b * a.n_pt_q + qt) * KT_CAP * KT_PTS + t;
+            int out = 0;
+            for (int i = 0; i < cnt; ++i) {
+                if (sh.stash_d[i][t] <= thr) {
+                    if (out < KT_CAP) cl[(size_t)out * KT_PTS] = sh.stash_i[i][t];
+                    ++out;
+                }
+            }
+            a.cnt[((size_t)b * a.n_pt_q + qt) * KT_PTS + t] = (overflow || out > KT_CAP) ? -1 : out;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(KT_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace
+
+int launch_knn_pack(const float* f, int B, int D, int N, float* img, float* nrm, float* pm, cudaStream_t st) {
+    LS_REQUIRE(f && img && nrm && pm && B >= 1 && D >= 1 && N >= 1, "knn_pack: bad arguments");
+    const int n_pt = knn_tc_tiles(N), n_kb = knn_tc_kblocks(D);
+    k_knn_pack<<<dim3(n_pt, B), KT_PTS, 0, st>>>(f, D, N, n_pt, n_kb, img, nrm, pm);
+    LS_CHECK_LAUNCH("k_knn_pack");
+    return LS_OK;
+}
+
+int launch_knn_tc(const KnnTcArgs& a, int B, cudaStream_t st) {
+    LS_REQUIRE(a.img_s && a.img_q && a.nrm_s && a.nrm_q && a.cand && a.cnt, "knn_tc: null pointer");
+    LS_REQUIRE(a.Ns >= LS_KNN_K && a.Ns <= 65535 && a.Nd >= 1, "knn_tc: need 16 <= Ns <= 65535");
+    const size_t smem = sizeof(KtShared) + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_knn_tc<<<dim3(a.n_pt_q, B), KT_THREADS, smem, st>>>(a);
+    LS_CHECK_LAUNCH("k_knn_tc");
+    return LS_OK;
+}
+
+}  // namespace ls
