@@ -19,6 +19,7 @@ LIB = os.path.join(HERE, "_ls_b200.so")
 SOURCES = ["ls_encoder.cu", "ls_gemm.cu", "ls_gemm_tc.cu", "ls_knn_tc.cu", "ls_solvers.cu", "ls_sdf.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+NVCC_FLAGS += os.environ.get("LS_NVCC_EXTRA", "").split()  # experiment knobs (-D...), part of the object digest
 
 
 def _nvcc() -> str:

@@ -37,11 +37,21 @@ namespace {
 
 constexpr int KT_IMG = KT_PTS * KT_KB;  // floats per hi (or lo) image of one block
 constexpr int KT_BLOCK = 2 * KT_IMG;    // hi + lo: 2048 floats = 8 KB
-constexpr int KT_GT = 4;                // source tiles per group (4 x 128 = 512 TMEM columns)
-constexpr int KT_STAGES = 3;
-constexpr int KT_STASH = 80;            // shared-memory stash slots per query
+#ifndef KT_GT_N
+#define KT_GT_N 2
+#endif
+constexpr int KT_GT = KT_GT_N;          // source tiles per group (each 128 TMEM columns)
+#ifndef KT_STAGES_N
+#define KT_STAGES_N 2
+#endif
+#ifndef KT_STASH_N
+#define KT_STASH_N 56
+#endif
+constexpr int KT_STAGES = KT_STAGES_N;
+constexpr int KT_STASH = KT_STASH_N;    // shared-memory stash slots per query
 constexpr int KT_THREADS = 160;
-constexpr int KT_TMEM_COLS = 512;
+constexpr int KT_TMEM_COLS = KT_GT * KT_PTS;  // 256 columns: two CTAs share an SM's tensor memory
+constexpr int KT_MIN_CTAS = KT_GT <= 2 ? 2 : 1;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -96,19 +106,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+#define KT_V32(c, v)                                                                                              \
+    c(v[0]), c(v[1]), c(v[2]), c(v[3]), c(v[4]), c(v[5]), c(v[6]), c(v[7]), c(v[8]), c(v[9]), c(v[10]), c(v[11]),  \
+        c(v[12]), c(v[13]), c(v[14]), c(v[15]), c(v[16]), c(v[17]), c(v[18]), c(v[19]), c(v[20]), c(v[21]), c(v[22]), \
+        c(v[23]), c(v[24]), c(v[25]), c(v[26]), c(v[27]), c(v[28]), c(v[29]), c(v[30]), c(v[31])
+#define KT_OUT(x) "=r"(x)
+#define KT_INOUT(x) "+r"(x)
+// asynchronous TMEM load of 32 columns of this thread's lane; the registers are valid after tmem_ld_wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : KT_V32(KT_OUT, v)
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-
+// waits for every outstanding tcgen05.ld of the thread; the in/out operands tie the consumers of v to the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : KT_V32(KT_INOUT, v)::"memory");
+}
 // ------------------------------------------------------------------------------------------- pack
 __global__ void __launch_bounds__(KT_PTS) k_knn_pack(const float* __restrict__ f, int D, int N, int n_pt, int n_kb,
                                                      float* __restrict__ img, float* __restrict__ nrm,
@@ -150,8 +166,7 @@ __global__ void __launch_bounds__(KT_PTS) k_knn_pack(const float* __restrict__ f
 struct KtShared {
     float stage[KT_STAGES][1 + KT_GT][KT_BLOCK];  // [stage][0 = query tile, 1.. = source tiles][hi | lo]
     float ns[2][KT_GT * KT_PTS];                  // squared norms of the current group's sources
-    float stash_d[KT_STASH][KT_PTS];
-    unsigned short stash_i[KT_STASH][KT_PTS];
+    float2 stash[KT_STASH][KT_PTS];               // per query (column) {dt, source index bits}
     float red[4];
     uint64_t full[KT_STAGES], empty[KT_STAGES], tmem_full, tmem_empty;
     uint32_t tmem_base;
@@ -181,9 +196,9 @@ __device__ __forceinline__ float kth16_of_32(const float* m) {
     return a[15];
 }
 
-__global__ void __launch_bounds__(KT_THREADS, 1) k_knn_tc(const KnnTcArgs a) {
+__global__ void __launch_bounds__(KT_THREADS, KT_MIN_CTAS) k_knn_tc(const KnnTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    KtShared& sh = *reinterpret_cast<KtShared*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    KtShared& sh = *reinterpret_cast<KtShared*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int b = blockIdx.y, qt = blockIdx.x;
     const int n_groups = (a.n_pt_s + KT_GT - 1) / KT_GT;
@@ -272,27 +287,30 @@ __global__ void __launch_bounds__(KT_THREADS, 1) k_knn_tc(const KnnTcArgs a) {
         float m[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) m[j] = inf;
-        int cnt = 0;
         bool overflow = false;
         float thr = inf;
         const uint32_t tlane = tmem + ((uint32_t)(w * 32) << 16);
+        // stash of this query: 8-byte entries {dt, source index}, slot stride = 128 entries
+        constexpr uint32_t SLOT_B = KT_PTS * 8;
+        const uint32_t st_base = smem_u32(&sh.stash[0][t]);
+        const uint32_t st_guard = st_base + (KT_STASH - 8) * SLOT_B;  // fewer than 8 free slots beyond this address
+        uint32_t st_addr = st_base;
 
         for (int g = 0; g < n_groups; ++g) {
             const int tiles = min(KT_GT, a.n_pt_s - g * KT_GT);
             const int ncols = tiles * KT_PTS;
-            float* ns = sh.ns[g & 1];
+            const float* ns = sh.ns[g & 1];
             {
                 const float* nsg = a.nrm_s + ((size_t)b * a.n_pt_s + g * KT_GT) * KT_PTS;
-                if (t * 4 < ncols) *reinterpret_cast<float4*>(ns + t * 4) = __ldg(reinterpret_cast<const float4*>(nsg + t * 4));
+                if (t * 4 < ncols)
+                    *reinterpret_cast<float4*>(&sh.ns[g & 1][t * 4]) = __ldg(reinterpret_cast<const float4*>(nsg + t * 4));
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             mbar_wait(&sh.tmem_full, g & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // ---- sweep 1: group minima (group = column mod 32)
-            for (int c = 0; c < ncols; c += 32) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld32(tlane + (uint32_t)c, v);
+            uint32_t va[32], vb[32];
+            // ---- sweep 1: group minima (group = column mod 32); TMEM loads run one 32-column chunk ahead
+            auto minima = [&](const uint32_t* v, int c) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                     const float4 n4 = *reinterpret_cast<const float4*>(ns + c + 4 * j4);
@@ -301,46 +319,105 @@ __global__ void __launch_bounds__(KT_THREADS, 1) k_knn_tc(const KnnTcArgs a) {
                     m[4 * j4 + 2] = fminf(m[4 * j4 + 2], fmaf(-2.f, __uint_as_float(v[4 * j4 + 2]), n4.z));
                     m[4 * j4 + 3] = fminf(m[4 * j4 + 3], fmaf(-2.f, __uint_as_float(v[4 * j4 + 3]), n4.w));
                 }
+            };
+            __syncwarp();
+            tmem_ld32_issue(tlane, va);
+            for (int c = 0; c < ncols; c += 64) {  // ncols is a multiple of 128
+                tmem_ld_wait(va);
+                tmem_ld32_issue(tlane + (uint32_t)(c + 32), vb);
+                minima(va, c);
+                tmem_ld_wait(vb);
+                tmem_ld32_issue(tlane + (uint32_t)((c + 64 < ncols) ? c + 64 : 0), va);  // last one re-reads chunk 0 for sweep 2
+                minima(vb, c + 32);
             }
-            thr = kth16_of_32(m) + e2;
-            // ---- sweep 2: everything that may still belong to the exact top-16 goes to the stash
-            for (int c = 0; c < ncols; c += 32) {
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld32(tlane + (uint32_t)c, v);
+            thr = valid ? kth16_of_32(m) + e2 : -inf;
+            if (g > 0) {
+                // the threshold only tightens: drop the stash entries that no longer qualify (keeps the stash short,
+                // and after the last group every entry satisfies the final threshold)
+                const int cnt = (int)((st_addr - st_base) / SLOT_B);
+                int o = 0;
+                for (int i = 0; i < cnt; ++i) {
+                    const float2 e = sh.stash[i][t];
+                    if (e.x <= thr) sh.stash[o++][t] = e;
+                }
+                st_addr = st_base + (uint32_t)o * SLOT_B;
+            }
+            // ---- sweep 2: everything that may still belong to the exact top-16 goes to the stash.
+            //      Branch-free: a predicated 8-byte shared store and a predicated pointer bump per source.
+            auto collect = [&](const uint32_t* v, int c) {
+                const uint32_t idx0 = (uint32_t)(g * KT_GT * KT_PTS + c);
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 n4 = *reinterpret_cast<const float4*>(ns + c + 4 * j4);
-                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    if (st_addr > st_guard) {  // stash nearly full: give up on this query (exact brute force later)
+                        overflow = true;
+                        st_addr = st_base;
+                    }
+                    const float4 n0 = *reinterpret_cast<const float4*>(ns + c + 8 * j8);
+                    const float4 n1 = *reinterpret_cast<const float4*>(ns + c + 8 * j8 + 4);
+                    const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float dt = fmaf(-2.f, __uint_as_float(v[4 * j4 + jj]), nn[jj]);
-                        if (dt <= thr && valid) {
-                            if (cnt < KT_STASH) {
-                                sh.stash_d[cnt][t] = dt;
-                                sh.stash_i[cnt][t] = (unsigned short)(g * KT_GT * KT_PTS + c + 4 * j4 + jj);
-                                ++cnt;
-                            } else {
-                                overflow = true;
-                            }
-                        }
+                    for (int j4 = 0; j4 < 2; ++j4) {
+                        // four sources at a time: the slot addresses are a prefix sum of the pass predicates, so
+                        // the four predicated stores do not wait on each other's pointer bump
+                        float dt[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            dt[jj] = fmaf(-2.f, __uint_as_float(v[8 * j8 + 4 * j4 + jj]), nn[4 * j4 + jj]);
+                        const uint32_t i0 = idx0 + (uint32_t)(8 * j8 + 4 * j4);
+                        asm volatile(
+                            "{\n\t"
+                            ".reg .pred p0, p1, p2, p3;\n\t"
+                            ".reg .u32 a1, a2, a3, i1, i2, i3, t;\n\t"
+                            ".reg .f32 f0, f1, f2, f3;\n\t"
+                            "mov.b32 f0, %1;\n\t"
+                            "mov.b32 f1, %2;\n\t"
+                            "mov.b32 f2, %3;\n\t"
+                            "mov.b32 f3, %4;\n\t"
+                            "setp.le.f32 p0, f0, %5;\n\t"
+                            "setp.le.f32 p1, f1, %5;\n\t"
+                            "setp.le.f32 p2, f2, %5;\n\t"
+                            "setp.le.f32 p3, f3, %5;\n\t"
+                            "selp.u32 t, %7, 0, p0;\n\t"
+                            "add.u32 a1, %0, t;\n\t"
+                            "selp.u32 t, %7, 0, p1;\n\t"
+                            "add.u32 a2, a1, t;\n\t"
+                            "selp.u32 t, %7, 0, p2;\n\t"
+                            "add.u32 a3, a2, t;\n\t"
+                            "add.u32 i1, %6, 1;\n\t"
+                            "add.u32 i2, %6, 2;\n\t"
+                            "add.u32 i3, %6, 3;\n\t"
+                            "@p0 st.shared.v2.b32 [%0], {%1, %6};\n\t"
+                            "@p1 st.shared.v2.b32 [a1], {%2, i1};\n\t"
+                            "@p2 st.shared.v2.b32 [a2], {%3, i2};\n\t"
+                            "@p3 st.shared.v2.b32 [a3], {%4, i3};\n\t"
+                            "selp.u32 t, %7, 0, p3;\n\t"
+                            "add.u32 %0, a3, t;\n\t"
+                            "}"
+                            : "+r"(st_addr)
+                            : "r"(__float_as_uint(dt[0])), "r"(__float_as_uint(dt[1])), "r"(__float_as_uint(dt[2])),
+                              "r"(__float_as_uint(dt[3])), "f"(thr), "r"(i0), "n"(SLOT_B)
+                            : "memory");
                     }
                 }
+            };
+            for (int c = 0; c < ncols; c += 64) {
+                tmem_ld_wait(va);
+                tmem_ld32_issue(tlane + (uint32_t)(c + 32), vb);
+                collect(va, c);
+                tmem_ld_wait(vb);
+                if (c + 64 < ncols) tmem_ld32_issue(tlane + (uint32_t)(c + 64), va);
+                collect(vb, c + 32);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&sh.tmem_empty);
         }
-        // ---- final filter with the tightest threshold -> global candidate list [b][qt][slot][128]
+        // ---- stash -> global candidate list [b][qt][slot][128]
         if (valid) {
             unsigned short* cl = a.cand + ((size_t)b * a.n_pt_q + qt) * KT_CAP * KT_PTS + t;
-            int out = 0;
-            for (int i = 0; i < cnt; ++i) {
-                if (sh.stash_d[i][t] <= thr) {
-                    if (out < KT_CAP) cl[(size_t)out * KT_PTS] = sh.stash_i[i][t];
-                    ++out;
-                }
-            }
-            a.cnt[((size_t)b * a.n_pt_q + qt) * KT_PTS + t] = (overflow || out > KT_CAP) ? -1 : out;
+            const int cnt = (int)((st_addr - st_base) / SLOT_B);
+            const int n = min(cnt, KT_CAP);
+            for (int i = 0; i < n; ++i) cl[(size_t)i * KT_PTS] = (unsigned short)__float_as_uint(sh.stash[i][t].y);
+            a.cnt[((size_t)b * a.n_pt_q + qt) * KT_PTS + t] = (overflow || cnt > KT_CAP) ? -1 : cnt;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
