@@ -166,6 +166,16 @@ LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 pa
 LS_API int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns,
            int64_t* idx, float* dist2, void* stream);
 
+/* The same graph through the path ls_encoder_forward uses for Ns > 128: tcgen05 3xTF32 candidate filter
+ * (ranking value |s|^2 - 2<q,s>, threshold = 16th smallest group minimum + error budget) followed by the exact
+ * fp32 direct-form re-rank of the candidates; a query whose candidate list overflows is brute-forced exactly.
+ * Results are identical to ls_knn.  n_candidates: optional [B,Nq] int32, candidates re-ranked per query
+ * (-1 = overflow -> brute force).  workspace: ls_knn_tc_workspace_bytes. */
+LS_API int ls_knn_tc_workspace_bytes(int32_t B, int32_t D, int32_t Nq, int32_t Ns, size_t* bytes);
+LS_API int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns,
+              int64_t* idx, float* dist2, int32_t* n_candidates, void* workspace, size_t workspace_bytes,
+              void* stream);
+
 /* pytorch3d.ops.sample_farthest_points(points, K=n_out), random_start_point=False
  * (vec_dgcnn_atten.py:169; model_utils.py:205; more_solver.py:67,107-108).
  * xyz [B,3,N] -> idx [B,n_out] int64, optional out_xyz [B,3,n_out]. */

@@ -595,6 +595,83 @@ int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_
     return launch_edge(MODE_KNN_ONLY, ea, static_cast<cudaStream_t>(stream));
 }
 
+// the same graph through the tensor-core candidate filter + exact re-rank (what ls_encoder_forward runs)
+static void knn_tc_plan(int B, int D, int Nq, int Ns, void* ws, float** img_s, float** nrm_s, float** pm_s, float** img_q,
+                        float** nrm_q, float** pm_q, unsigned short** cand, int** cnt, size_t* bytes) {
+    Carver c(ws);
+    *img_s = c.take<float>((size_t)B * knn_tc_img_floats(Ns, D));
+    *nrm_s = c.take<float>((size_t)B * knn_tc_nrm_floats(Ns));
+    *pm_s = c.take<float>((size_t)B * knn_tc_pm_floats(Ns, D));
+    *img_q = c.take<float>((size_t)B * knn_tc_img_floats(Nq, D));
+    *nrm_q = c.take<float>((size_t)B * knn_tc_nrm_floats(Nq));
+    *pm_q = c.take<float>((size_t)B * knn_tc_pm_floats(Nq, D));
+    *cand = c.take<unsigned short>((size_t)B * knn_tc_cand_u16(Nq));
+    *cnt = c.take<int>((size_t)B * knn_tc_nrm_floats(Nq));
+    *bytes = (c.off + 255) & ~size_t(255);
+}
+int ls_knn_tc_workspace_bytes(int32_t B, int32_t D, int32_t Nq, int32_t Ns, size_t* bytes) {
+    LS_REQUIRE(bytes && B >= 1 && D >= 1 && Nq >= 1 && Ns >= 1, "bad arguments");
+    float *a, *b, *c, *d, *e, *f;
+    unsigned short* g;
+    int* h;
+    knn_tc_plan(B, D, Nq, Ns, nullptr, &a, &b, &c, &d, &e, &f, &g, &h, bytes);
+    return LS_OK;
+}
+int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns, int64_t* idx,
+              float* dist2, int32_t* n_candidates, void* workspace, size_t workspace_bytes, void* stream) {
+    LS_REQUIRE(query && source && idx && workspace, "null pointer");
+    LS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && Nq >= 1 && Ns >= LS_KNN_K && Ns <= 65535, "bad sizes (need 16 <= Ns <= 65535)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    KnnTcArgs ka{};
+    EdgeArgs ea{};
+    float *img_s, *nrm_s, *pm_s, *img_q, *nrm_q, *pm_q;
+    unsigned short* cand;
+    int* cnt;
+    size_t need;
+    knn_tc_plan(B, D, Nq, Ns, workspace, &img_s, &nrm_s, &pm_s, &img_q, &nrm_q, &pm_q, &cand, &cnt, &need);
+    if (need > workspace_bytes) {
+        set_error("workspace too small");
+        return LS_ERR_WORKSPACE;
+    }
+    int rc = launch_knn_pack(source, B, D, Ns, img_s, nrm_s, pm_s, st);
+    if (rc != LS_OK) return rc;
+    rc = launch_knn_pack(query, B, D, Nq, img_q, nrm_q, pm_q, st);
+    if (rc != LS_OK) return rc;
+    ka.img_s = img_s;
+    ka.nrm_s = nrm_s;
+    ka.img_q = img_q;
+    ka.nrm_q = nrm_q;
+    ka.Ns = Ns;
+    ka.Nd = Nq;
+    ka.n_pt_s = knn_tc_tiles(Ns);
+    ka.n_pt_q = knn_tc_tiles(Nq);
+    ka.n_kb = knn_tc_kblocks(D);
+    ka.kappa = g_knn_tc_kappa_scale * knn_tc_kappa(D);
+    ka.cand = cand;
+    ka.cnt = cnt;
+    rc = launch_knn_tc(ka, B, st);
+    if (rc != LS_OK) return rc;
+    if (n_candidates)
+        LS_CHECK_CUDA(cudaMemcpy2DAsync(n_candidates, sizeof(int) * Nq, cnt, sizeof(int) * ka.n_pt_q * KT_PTS, sizeof(int) * Nq, B,
+                                        cudaMemcpyDeviceToDevice, st));
+    ea.src_f = source;
+    ea.dst_f = query;
+    ea.B = B;
+    ea.D = D;
+    ea.Ns = Ns;
+    ea.Nd = Nq;
+    ea.Co = 32;
+    ea.idx_out = idx;
+    ea.dist_out = dist2;
+    ea.cand = cand;
+    ea.cand_cnt = cnt;
+    ea.pm_s = pm_s;
+    ea.pm_q = pm_q;
+    ea.Dp = ka.n_kb * KT_KB;
+    ea.qpc = pick_qpc(B, Nq, true);
+    return launch_edge(MODE_KNN_ONLY, ea, st);
+}
+
 int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz,
            void* stream) {
     LS_REQUIRE(xyz && idx, "null pointer");

@@ -6,6 +6,8 @@
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 
 from . import _lib
@@ -51,6 +53,29 @@ def knn_graph_cm(query_cm: torch.Tensor, source_cm: torch.Tensor):
         _lib.check(rc, "ls_knn")
         _lib.launch_count += 1
     return idx, d2
+
+
+@torch.no_grad()
+def knn_graph_cm_tc(query_cm: torch.Tensor, source_cm: torch.Tensor):
+    """knn_graph_cm through the tensor-core candidate filter + exact re-rank (the encoder's path for Ns > 128).
+    -> (idx [B,Nq,16] int64, dist2 [B,Nq,16], n_candidates [B,Nq] int32; -1 = overflow, brute-forced)."""
+    _lib.require_cuda(query_cm, "query")
+    B, D, Nq = query_cm.shape
+    Ns = source_cm.shape[2]
+    q = query_cm.detach().float().contiguous()
+    s = source_cm.detach().float().contiguous()
+    idx = torch.empty(B, Nq, _lib.LS_KNN_K, dtype=torch.int64, device=q.device)
+    d2 = torch.empty(B, Nq, _lib.LS_KNN_K, dtype=torch.float32, device=q.device)
+    nc = torch.empty(B, Nq, dtype=torch.int32, device=q.device)
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.lib().ls_knn_tc_workspace_bytes(B, D, Nq, Ns, C.byref(nbytes)), "ls_knn_tc_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=q.device)
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().ls_knn_tc(q.data_ptr(), s.data_ptr(), B, D, Nq, Ns, idx.data_ptr(), d2.data_ptr(), nc.data_ptr(),
+                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(q.device))
+        _lib.check(rc, "ls_knn_tc")
+        _lib.launch_count += 1
+    return idx, d2, nc
 
 
 @torch.no_grad()

@@ -105,6 +105,102 @@ def test_knn_edge_cases(dev):
     assert torch.equal(idx.cpu(), ridx)
 
 
+# ------------------------------------------------------------------------------------------ tensor-core kNN
+@pytest.mark.parametrize("tag", ["random", "shipped"])
+def test_knn_tc_teacher_forced_equals_exact(tag, dev, oracle_R):
+    """ls_knn_tc (tcgen05 candidate filter + exact re-rank) fed the oracle's layer inputs returns exactly what
+    the brute-force ls_knn returns -- indices AND squared distances bit for bit -- and the oracle's graph."""
+    from livingscenes_b200.ops import knn_graph_cm, knn_graph_cm_tc
+
+    sd = state_dict_for(tag)
+    g = golden(f"encoder_{tag}")
+    xn = torch.from_numpy(g["x_norm"])
+    tr = {}
+    with torch.no_grad():
+        oracle_R.encoder_forward(sd, xn, trace=tr)
+    for i in range(7):
+        sf, df = tr["src_f"][i], tr["dst_f"][i]
+        B, C, _, Ns = sf.shape
+        q, s = df.reshape(B, C * 3, -1).to(dev), sf.reshape(B, C * 3, Ns).to(dev)
+        idx_e, d_e = knn_graph_cm(q, s)
+        idx_t, d_t, nc = knn_graph_cm_tc(q, s)
+        torch.cuda.synchronize()
+        assert torch.equal(idx_e, idx_t), f"layer {i}: tensor-core graph differs from the brute-force graph"
+        assert torch.equal(d_e, d_t), f"layer {i}: re-ranked distances differ bitwise"
+        assert int(nc.min()) >= 16 and int(nc.max()) <= 64, f"layer {i}: candidate counts {int(nc.min())}..{int(nc.max())}"
+        bad, ndiff, nrows = _knn_rows_equivalent(idx_t, tr["knn_idx"][i], df, sf)
+        assert bad == 0
+        print(f"[{tag}] layer {i}: candidates per query mean {float(nc.float().mean()):.1f} max {int(nc.max())}")
+
+
+@pytest.mark.parametrize("B,D,Nq,Ns", [(2, 3, 300, 300), (3, 96, 1000, 1000), (1, 96, 512, 1024), (2, 192, 128, 512),
+                                       (1, 8, 130, 2500), (2, 384, 40, 200), (1, 5, 16, 16)])
+def test_knn_tc_shapes_and_ties(B, D, Nq, Ns, dev):
+    """Ragged tiles (Nq, Ns not multiples of 128, D not a multiple of 8), exact ties from duplicated sources
+    (lower index first), and a badly conditioned cloud (far from the origin: the filter's error budget exceeds
+    the neighbour distances, lists overflow, the exact brute-force fallback takes over)."""
+    from livingscenes_b200.ops import knn_graph_cm, knn_graph_cm_tc
+
+    g = torch.Generator().manual_seed(B * 1000 + Nq)
+    s = torch.randn(B, D, Ns, generator=g)
+    if Ns > 40:
+        s[:, :, 17] = s[:, :, 5]
+        s[:, :, Ns - 3] = s[:, :, 5]
+    q = s[:, :, :Nq].clone() if Nq <= Ns else torch.randn(B, D, Nq, generator=g)
+    for shift in (0.0, 300.0):
+        qq, ss = (q + shift).to(dev), (s + shift).to(dev)
+        idx_e, d_e = knn_graph_cm(qq, ss)
+        idx_t, d_t, nc = knn_graph_cm_tc(qq, ss)
+        torch.cuda.synchronize()
+        assert torch.equal(idx_e, idx_t), f"shift {shift}: graphs differ"
+        assert torch.equal(d_e, d_t)
+        if shift == 0.0 and Ns > 40 and Nq > 5:
+            assert idx_t[0, 5, :3].tolist() == [5, 17, Ns - 3]
+        print(f"shift {shift}: overflowed queries {int((nc < 0).sum())}/{nc.numel()}, max candidates {int(nc.max())}")
+
+
+def test_knn_tc_overflow_fallback_is_exact(dev):
+    """kappa_scale = 1e6 makes every candidate list overflow: the brute-force fallback must reproduce ls_knn."""
+    from livingscenes_b200 import _lib
+    from livingscenes_b200.ops import knn_graph_cm, knn_graph_cm_tc
+
+    g = torch.Generator().manual_seed(11)
+    s = torch.randn(2, 96, 700, generator=g).to(dev)
+    q = torch.randn(2, 96, 260, generator=g).to(dev)
+    idx_e, d_e = knn_graph_cm(q, s)
+    try:
+        _lib.set_knn_tensor_cores(True, 1e6)
+        idx_t, d_t, nc = knn_graph_cm_tc(q, s)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_knn_tensor_cores(True, 1.0)
+    assert int((nc >= 0).sum()) == 0
+    assert torch.equal(idx_e, idx_t) and torch.equal(d_e, d_t)
+
+
+@pytest.mark.parametrize("tag", ["random", "shipped"])
+@pytest.mark.parametrize("B,N", [(4, 1024), (2, 2048), (3, 1000)])
+def test_encoder_knn_tc_equals_brute_force(tag, B, N, dev, oracle_R):
+    """Whole encoder with the tensor-core graph vs the brute-force graph: identical indices at all 7 layers and
+    bit-identical embeddings (the two paths feed the same arithmetic downstream)."""
+    from livingscenes_b200 import _lib
+
+    enc = _model(tag, dev).encoder
+    x = oracle_R.synth_instances(B, N, 555 + N).to(dev)
+    try:
+        _lib.set_knn_tensor_cores(False, 1.0)
+        a = enc.run(x, normalize=True, taps=True)
+        _lib.set_knn_tensor_cores(True, 1.0)
+        b = enc.run(x, normalize=True, taps=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_knn_tensor_cores(True, 1.0)
+    for i, (ia, ib) in enumerate(zip(a["knn_idx"], b["knn_idx"])):
+        assert torch.equal(ia, ib), f"layer {i}"
+    for k in ("z_so3", "z_inv", "scale", "center"):
+        assert torch.equal(a[k], b[k]), k
+
+
 @pytest.mark.parametrize("N,n_out", [(1024, 512), (2048, 1024), (1000, 77), (5000, 1024), (16, 16)])
 def test_fps_bit_exact(N, n_out, dev, oracle_R):
     from livingscenes_b200.ops import farthest_point_sample
