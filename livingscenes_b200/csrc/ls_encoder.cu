@@ -71,7 +71,9 @@ struct Plan {
     // tensor-core kNN filter (ls_knn_tc.cu): packed images / norms / point-major copies and candidate lists
     float *kimg_s, *knrm_s, *kpm_s, *kimg_q, *knrm_q, *kpm_q;
     unsigned short* kcand;
+    float *kcand_dt, *ke2;
     int* kcnt;
+    int64_t* kidx;
     int* sel[LS_MAX_LAYERS];
     size_t bytes;
 };
@@ -163,7 +165,10 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
     p.knrm_q = c.take<float>((size_t)B * std::max<size_t>(knrm_q, 1));
     p.kpm_q = c.take<float>((size_t)B * std::max<size_t>(kpm_q, 1));
     p.kcand = c.take<unsigned short>((size_t)B * std::max<size_t>(kcand, 1));
+    p.kcand_dt = c.take<float>((size_t)B * std::max<size_t>(kcand, 1));
     p.kcnt = c.take<int>((size_t)B * std::max<size_t>(knrm_s + knrm_q, 1));
+    p.ke2 = c.take<float>((size_t)B * std::max<size_t>(knrm_s + knrm_q, 1));
+    p.kidx = c.take<int64_t>((size_t)B * std::max<size_t>(knrm_s + knrm_q, 1) * LS_KNN_K);
     for (int i = 0; i < d->num_layers; ++i)
         p.sel[i] = d->layers[i].down_factor > 1 ? c.take<int>((size_t)B * p.n_dst[i]) : nullptr;
     p.bytes = (c.off + 255) & ~size_t(255);
@@ -374,14 +379,15 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ka.nrm_s = p.knrm_s;
             ka.img_q = p.kimg_s;
             ka.nrm_q = p.knrm_s;
-            ea.pm_s = p.kpm_s;
-            ea.pm_q = p.kpm_s;
+            RerankArgs ra{};
+            ra.pm_s = p.kpm_s;
+            ra.pm_q = p.kpm_s;
             if (L.down_factor > 1) {
                 rc = launch_knn_pack(dst_f, B, D, Nd, p.kimg_q, p.knrm_q, p.kpm_q, st);
                 if (rc != LS_OK) return rc;
                 ka.img_q = p.kimg_q;
                 ka.nrm_q = p.knrm_q;
-                ea.pm_q = p.kpm_q;
+                ra.pm_q = p.kpm_q;
             }
             ka.Ns = Ns;
             ka.Nd = Nd;
@@ -390,14 +396,26 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ka.n_kb = knn_tc_kblocks(D);
             ka.kappa = g_knn_tc_kappa_scale * knn_tc_kappa(D);
             ka.cand = p.kcand;
+            ka.cand_dt = p.kcand_dt;
             ka.cnt = p.kcnt;
+            ka.e2 = p.ke2;
             rc = launch_knn_tc(ka, B, st);
             if (rc != LS_OK) return rc;
-            ea.cand = p.kcand;
-            ea.cand_cnt = p.kcnt;
-            ea.Dp = ka.n_kb * KT_KB;
+            ra.cand = p.kcand;
+            ra.cand_dt = p.kcand_dt;
+            ra.cand_cnt = p.kcnt;
+            ra.e2 = p.ke2;
+            ra.Ns = Ns;
+            ra.Nd = Nd;
+            ra.Dp = ka.n_kb * KT_KB;
+            ra.idx_out = p.kidx;
+            ra.idx_tap = io->knn_idx[i];
+            k_knn_rerank<<<dim3((Nd + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B), RR_WARPS * 32, 0, st>>>(ra);
+            LS_CHECK_LAUNCH("k_knn_rerank");
+            ea.idx_in = p.kidx;
+            ea.idx_out = nullptr;
         }
-        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr || ea.cand != nullptr);
+        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr);
         if (i == 0) {
             ea.w0 = L.w0;
             ProfScope ps(4, i, st);
@@ -597,7 +615,8 @@ int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_
 
 // the same graph through the tensor-core candidate filter + exact re-rank (what ls_encoder_forward runs)
 static void knn_tc_plan(int B, int D, int Nq, int Ns, void* ws, float** img_s, float** nrm_s, float** pm_s, float** img_q,
-                        float** nrm_q, float** pm_q, unsigned short** cand, int** cnt, size_t* bytes) {
+                        float** nrm_q, float** pm_q, unsigned short** cand, int** cnt, float** cand_dt, float** e2,
+                        size_t* bytes) {
     Carver c(ws);
     *img_s = c.take<float>((size_t)B * knn_tc_img_floats(Ns, D));
     *nrm_s = c.take<float>((size_t)B * knn_tc_nrm_floats(Ns));
@@ -607,14 +626,16 @@ static void knn_tc_plan(int B, int D, int Nq, int Ns, void* ws, float** img_s, f
     *pm_q = c.take<float>((size_t)B * knn_tc_pm_floats(Nq, D));
     *cand = c.take<unsigned short>((size_t)B * knn_tc_cand_u16(Nq));
     *cnt = c.take<int>((size_t)B * knn_tc_nrm_floats(Nq));
+    *cand_dt = c.take<float>((size_t)B * knn_tc_cand_u16(Nq));
+    *e2 = c.take<float>((size_t)B * knn_tc_nrm_floats(Nq));
     *bytes = (c.off + 255) & ~size_t(255);
 }
 int ls_knn_tc_workspace_bytes(int32_t B, int32_t D, int32_t Nq, int32_t Ns, size_t* bytes) {
     LS_REQUIRE(bytes && B >= 1 && D >= 1 && Nq >= 1 && Ns >= 1, "bad arguments");
-    float *a, *b, *c, *d, *e, *f;
+    float *a, *b, *c, *d, *e, *f, *i, *j;
     unsigned short* g;
     int* h;
-    knn_tc_plan(B, D, Nq, Ns, nullptr, &a, &b, &c, &d, &e, &f, &g, &h, bytes);
+    knn_tc_plan(B, D, Nq, Ns, nullptr, &a, &b, &c, &d, &e, &f, &g, &h, &i, &j, bytes);
     return LS_OK;
 }
 int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int32_t Nq, int32_t Ns, int64_t* idx,
@@ -623,12 +644,11 @@ int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int
     LS_REQUIRE(B >= 1 && B <= 65535 && D >= 1 && Nq >= 1 && Ns >= LS_KNN_K && Ns <= 65535, "bad sizes (need 16 <= Ns <= 65535)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     KnnTcArgs ka{};
-    EdgeArgs ea{};
-    float *img_s, *nrm_s, *pm_s, *img_q, *nrm_q, *pm_q;
+    float *img_s, *nrm_s, *pm_s, *img_q, *nrm_q, *pm_q, *cand_dt, *e2;
     unsigned short* cand;
     int* cnt;
     size_t need;
-    knn_tc_plan(B, D, Nq, Ns, workspace, &img_s, &nrm_s, &pm_s, &img_q, &nrm_q, &pm_q, &cand, &cnt, &need);
+    knn_tc_plan(B, D, Nq, Ns, workspace, &img_s, &nrm_s, &pm_s, &img_q, &nrm_q, &pm_q, &cand, &cnt, &cand_dt, &e2, &need);
     if (need > workspace_bytes) {
         set_error("workspace too small");
         return LS_ERR_WORKSPACE;
@@ -648,28 +668,30 @@ int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int
     ka.n_kb = knn_tc_kblocks(D);
     ka.kappa = g_knn_tc_kappa_scale * knn_tc_kappa(D);
     ka.cand = cand;
+    ka.cand_dt = cand_dt;
     ka.cnt = cnt;
+    ka.e2 = e2;
     rc = launch_knn_tc(ka, B, st);
     if (rc != LS_OK) return rc;
     if (n_candidates)
         LS_CHECK_CUDA(cudaMemcpy2DAsync(n_candidates, sizeof(int) * Nq, cnt, sizeof(int) * ka.n_pt_q * KT_PTS, sizeof(int) * Nq, B,
                                         cudaMemcpyDeviceToDevice, st));
-    ea.src_f = source;
-    ea.dst_f = query;
-    ea.B = B;
-    ea.D = D;
-    ea.Ns = Ns;
-    ea.Nd = Nq;
-    ea.Co = 32;
-    ea.idx_out = idx;
-    ea.dist_out = dist2;
-    ea.cand = cand;
-    ea.cand_cnt = cnt;
-    ea.pm_s = pm_s;
-    ea.pm_q = pm_q;
-    ea.Dp = ka.n_kb * KT_KB;
-    ea.qpc = pick_qpc(B, Nq, true);
-    return launch_edge(MODE_KNN_ONLY, ea, st);
+    RerankArgs ra{};
+    ra.cand = cand;
+    ra.cand_dt = cand_dt;
+    ra.cand_cnt = cnt;
+    ra.e2 = e2;
+    ra.all_exact = dist2 != nullptr;
+    ra.pm_s = pm_s;
+    ra.pm_q = pm_q;
+    ra.Ns = Ns;
+    ra.Nd = Nq;
+    ra.Dp = ka.n_kb * KT_KB;
+    ra.idx_out = idx;
+    ra.dist_out = dist2;
+    k_knn_rerank<<<dim3((Nq + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B), RR_WARPS * 32, 0, st>>>(ra);
+    LS_CHECK_LAUNCH("k_knn_rerank");
+    return LS_OK;
 }
 
 int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz,

@@ -300,12 +300,6 @@ struct EdgeArgs {
     int64_t* idx_out;        // optional [B][Nd][16]
     const int64_t* idx_in;   // optional: graph given (teacher forcing, or built by k_knn_small)
     float* dist_out;         // optional [B][Nd][16] (MODE_KNN_ONLY)
-    // candidate lists of the tensor-core filter (ls_knn_tc.cu): exact re-rank replaces the brute-force phase 1
-    const unsigned short* cand;  // optional [B][ceil(Nd/128)][KT_CAP][128]
-    const int* cand_cnt;         // [B][ceil(Nd/128)*128], -1 = overflow -> brute force that query
-    const float* pm_s;           // [B][Ns][Dp] point-major fp32 features of the sources
-    const float* pm_q;           // [B][Nd][Dp] ... of the queries
-    int Dp;
 };
 
 // ---- warp-level top-k machinery.  A candidate is ONE 64-bit key: (float bits of the squared distance
@@ -410,69 +404,6 @@ __device__ __noinline__ SelRet knn_select_slow(u64 k0, u64 k1, u64 k2, u64 k3, u
     return SelRet{lk, cnt};
 }
 
-// ---- exact re-rank of the tensor-core candidates.  The squared distance is the reference's direct form
-//      sum_d (q_d - s_d)^2 accumulated with one fp32 FMA per dimension in ascending d -- the same operation
-//      sequence as the brute-force tiles above, so both paths produce bit-identical keys.
-__device__ __forceinline__ float exact_dist_pm(const float* __restrict__ qrow, const float* __restrict__ srow, int Dp) {
-    float acc = 0.f;
-#pragma unroll 4
-    for (int d = 0; d < Dp; d += 4) {
-        const float4 qv = __ldg(reinterpret_cast<const float4*>(qrow + d));
-        const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + d));
-        float df = __fsub_rn(qv.x, sv.x);
-        acc = __fmaf_rn(df, df, acc);
-        df = __fsub_rn(qv.y, sv.y);
-        acc = __fmaf_rn(df, df, acc);
-        df = __fsub_rn(qv.z, sv.z);
-        acc = __fmaf_rn(df, df, acc);
-        df = __fsub_rn(qv.w, sv.w);
-        acc = __fmaf_rn(df, df, acc);
-    }
-    return acc;
-}
-// one warp, one query: lanes = candidates (32 per round); returns the sorted list element of this lane
-__device__ __noinline__ u64 knn_rerank(const float* qrow, const float* pms, const unsigned short* cl, int cnt, int Dp) {
-    const int lane = threadIdx.x & 31;
-    u64 lk = KEY_MAX;
-    for (int r0 = 0; r0 < cnt; r0 += 32) {
-        const int slot = r0 + lane;
-        u64 key = KEY_MAX;
-        if (slot < cnt) {
-            const int s = (int)__ldg(cl + (size_t)slot * KT_PTS);
-            key = make_key(exact_dist_pm(qrow, pms + (size_t)s * Dp, Dp), s);
-        }
-        __syncwarp();
-        if (r0 == 0) {
-            bitonic_sort32(key, lane, false);
-            lk = key;
-        } else {
-            bitonic_sort32(key, lane, true);
-            lk = key < lk ? key : lk;
-            bitonic_merge32(lk, lane);
-        }
-    }
-    return lk;
-}
-// exact brute force of one query over all sources (candidate-list overflow; never taken on sane inputs)
-__device__ __noinline__ u64 knn_bruteforce_pm(const float* qrow, const float* pms, int Ns, int Dp) {
-    const int lane = threadIdx.x & 31;
-    u64 lk = KEY_MAX;
-    for (int s0 = 0; s0 < Ns; s0 += 32) {
-        const int s = s0 + lane;
-        u64 key = s < Ns ? make_key(exact_dist_pm(qrow, pms + (size_t)s * Dp, Dp), s) : KEY_MAX;
-        __syncwarp();
-        if (s0 == 0) {
-            bitonic_sort32(key, lane, false);
-            lk = key;
-        } else {
-            bitonic_sort32(key, lane, true);
-            lk = key < lk ? key : lk;
-            bitonic_merge32(lk, lane);
-        }
-    }
-    return lk;
-}
-
 template <int MODE, int CPL>
 __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) {
     // phase-1 tiles and phase-2 scratch share one buffer
@@ -495,22 +426,6 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
         for (int e = t; e < nq * LS_KNN_K; e += EDGE_THREADS) {
             int ql = e >> 4, k = e & 15;
             sIdx[ql][k] = (int)a.idx_in[((size_t)b * Nd + q0 + ql) * LS_KNN_K + k];
-        }
-    } else if (a.cand != nullptr) {
-        // ------------------------------------------------------------------ phase 1': exact re-rank
-        const int n_pt_q = (Nd + KT_PTS - 1) / KT_PTS;
-        const int qtile = q0 / KT_PTS, tq0 = q0 % KT_PTS;  // qpc divides 128: a CTA never straddles a tile
-        const unsigned short* cl = a.cand + ((size_t)b * n_pt_q + qtile) * KT_CAP * KT_PTS + tq0;
-        const int* cc = a.cand_cnt + ((size_t)b * n_pt_q + qtile) * KT_PTS + tq0;
-        const float* pms = a.pm_s + (size_t)b * Ns * a.Dp;
-        for (int ql = w; ql < nq; ql += EDGE_THREADS / 32) {
-            const float* qrow = a.pm_q + ((size_t)b * Nd + q0 + ql) * a.Dp;
-            const int c = __ldg(cc + ql);
-            const u64 lk = c < 0 ? knn_bruteforce_pm(qrow, pms, Ns, a.Dp) : knn_rerank(qrow, pms, cl + ql, c, a.Dp);
-            if (lane < LS_KNN_K) {
-                sIdx[ql][lane] = min(key_idx(lk) & 0x7fffffff, Ns - 1);
-                if (MODE == MODE_KNN_ONLY) sDist[ql][lane] = key_dist(lk);
-            }
         }
     } else {
         // ------------------------------------------------------------------ phase 1: kNN
@@ -981,6 +896,261 @@ __global__ void __launch_bounds__(256) k_knn_small(const float* __restrict__ src
     if (lane < LS_KNN_K) {
         idx_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = min(ai, Ns - 1);
         if (dist_out) dist_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = ad;
+    }
+}
+
+// ---- exact re-rank of the tensor-core candidates.  The squared distance is the reference's direct form
+//      sum_d (q_d - s_d)^2 accumulated with one fp32 FMA per dimension in ascending d -- the same operation
+//      sequence as the brute-force tiles above, so both paths produce bit-identical keys.
+//      A lane owns one candidate row ([Dp] contiguous floats); RR_F4 float4 loads are issued back to back before
+//      the dependent FMA chain consumes them (the rows are cold: one exposed miss per chunk instead of one per
+//      sector), the query chunk is staged in shared memory and read as a broadcast.
+constexpr int RR_F4 = 8;   // float4 loads in flight per lane (32 dims per chunk)
+__device__ __forceinline__ float exact_dist_pm(const float* __restrict__ qrow, float* __restrict__ sq,
+                                               const float* __restrict__ srow, bool on, int Dp) {
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+#pragma unroll 1
+    for (int d0 = 0; d0 < Dp; d0 += 4 * RR_F4) {
+        float4 sv[RR_F4];
+#pragma unroll
+        for (int i = 0; i < RR_F4; ++i)
+            if (on && d0 + 4 * i < Dp) sv[i] = __ldg(reinterpret_cast<const float4*>(srow + d0 + 4 * i));
+        __syncwarp();
+        if (lane < RR_F4 && d0 + 4 * lane < Dp)
+            *reinterpret_cast<float4*>(sq + 4 * lane) = __ldg(reinterpret_cast<const float4*>(qrow + d0 + 4 * lane));
+        __syncwarp();
+        if (on) {
+#pragma unroll
+            for (int i = 0; i < RR_F4; ++i) {
+                if (d0 + 4 * i < Dp) {
+                    const float4 qv = *reinterpret_cast<const float4*>(sq + 4 * i);
+                    float df = __fsub_rn(qv.x, sv[i].x);
+                    acc = __fmaf_rn(df, df, acc);
+                    df = __fsub_rn(qv.y, sv[i].y);
+                    acc = __fmaf_rn(df, df, acc);
+                    df = __fsub_rn(qv.z, sv[i].z);
+                    acc = __fmaf_rn(df, df, acc);
+                    df = __fsub_rn(qv.w, sv[i].w);
+                    acc = __fmaf_rn(df, df, acc);
+                }
+            }
+        }
+    }
+    return acc;
+}
+// one warp, one query: lanes = candidates (32 per round); returns the sorted list element of this lane
+__device__ __noinline__ u64 knn_rerank(const float* qrow, float* sq, const float* pms, const unsigned short* cl, int cnt,
+                                       int Dp) {
+    const int lane = threadIdx.x & 31;
+    u64 lk = KEY_MAX;
+    for (int r0 = 0; r0 < cnt; r0 += 32) {
+        const int slot = r0 + lane;
+        const bool on = slot < cnt;
+        const int s = on ? (int)__ldg(cl + (size_t)slot * KT_PTS) : 0;
+        const float d = exact_dist_pm(qrow, sq, pms + (size_t)s * Dp, on, Dp);
+        u64 key = on ? make_key(d, s) : KEY_MAX;
+        if (r0 == 0) {
+            bitonic_sort32(key, lane, false);
+            lk = key;
+        } else {
+            bitonic_sort32(key, lane, true);
+            lk = key < lk ? key : lk;
+            bitonic_merge32(lk, lane);
+        }
+    }
+    return lk;
+}
+// exact brute force of one query over all sources (candidate-list overflow; never taken on sane inputs)
+__device__ __noinline__ u64 knn_bruteforce_pm(const float* qrow, float* sq, const float* pms, int Ns, int Dp) {
+    const int lane = threadIdx.x & 31;
+    u64 lk = KEY_MAX;
+    for (int s0 = 0; s0 < Ns; s0 += 32) {
+        const int s = s0 + lane;
+        const bool on = s < Ns;
+        const float d = exact_dist_pm(qrow, sq, pms + (size_t)(on ? s : 0) * Dp, on, Dp);
+        u64 key = on ? make_key(d, s) : KEY_MAX;
+        if (s0 == 0) {
+            bitonic_sort32(key, lane, false);
+            lk = key;
+        } else {
+            bitonic_sort32(key, lane, true);
+            lk = key < lk ? key : lk;
+            bitonic_merge32(lk, lane);
+        }
+    }
+    return lk;
+}
+
+
+// Re-rank kernel: one warp per query, candidate lists from k_knn_tc (ls_knn_tc.cu) -> the final graph
+// idx [B][Nd][16] (ascending (distance, index)), optionally the squared distances.
+//   The candidates are first sorted by their tensor-core ranking value dt.  Two candidates whose dt differ by
+//   more than 2E are ordered like their exact fp32 distances (|dt + |q|^2 - d| <= E for both), so only RUNS of
+//   candidates chained by gaps <= 2E can be mis-ordered -- exact ties always are in one run.  Exact direct-form
+//   distances are computed for the runs that reach into the first 16 ranks only, and those runs are re-sorted
+//   by (exact distance, index); every other candidate keeps its rank.  ~1 candidate in 10 needs its feature
+//   row instead of all ~22.  Lists longer than 32 (rare) take the all-exact path, overflowed lists brute force.
+struct RerankArgs {
+    const unsigned short* cand;  // [B][ceil(Nd/128)][KT_CAP][128]
+    const float* cand_dt;        // same layout
+    const int* cand_cnt;         // [B][ceil(Nd/128)*128], -1 = overflow -> brute force that query
+    const float* e2;             // [B][ceil(Nd/128)*128]
+    const float* pm_s;           // [B][Ns][Dp] point-major fp32 features of the sources
+    const float* pm_q;           // [B][Nd][Dp] ... of the queries
+    int Ns, Nd, Dp;
+    int all_exact;               // 1: exact distance for every candidate (needed when dist_out is wanted)
+    int64_t* idx_out;            // [B][Nd][16] consumed by k_knn_edge (idx_in)
+    int64_t* idx_tap;            // optional second copy (API tap)
+    float* dist_out;             // optional [B][Nd][16]
+};
+constexpr int RR_WARPS = 8, RR_QPW = 4;  // warps per CTA, consecutive queries per warp
+constexpr int RR_DCH = 192, RR_NR = 4, RR_ROW = RR_DCH + 4;  // dims per chunk, rows per pass, padded row stride
+// Exact direct-form distances for the few lanes that `need` one: the warp loads the query chunk and up to RR_NR
+// needed candidate rows cooperatively (coalesced, all loads in flight together) into shared memory, then every
+// needing lane runs its sequential FMA chain out of shared memory.  Same operation order as exact_dist_pm.
+__device__ __forceinline__ float exact_dist_coop(bool need, int s, const float* __restrict__ qrow,
+                                                 const float* __restrict__ pms, int Dp, float* sm) {
+    const int lane = threadIdx.x & 31;
+    const unsigned mask = __ballot_sync(FULL, need);
+    const int my_rank = __popc(mask & ((1u << lane) - 1u)), n_need = __popc(mask);
+    float acc = 0.f;
+    unsigned rest = mask;
+    for (int base = 0; base < n_need; base += RR_NR) {
+        int src[RR_NR];
+#pragma unroll
+        for (int r = 0; r < RR_NR; ++r) {
+            const int l = rest ? __ffs(rest) - 1 : -1;
+            rest = rest ? rest & (rest - 1) : 0u;
+            src[r] = l >= 0 ? __shfl_sync(FULL, s, l) : -1;
+        }
+        const bool mine = need && my_rank >= base && my_rank < base + RR_NR;
+        for (int d0 = 0; d0 < Dp; d0 += RR_DCH) {
+            const int n4 = min(RR_DCH, Dp - d0) >> 2;
+            __syncwarp();
+            for (int i = lane; i < n4; i += 32) {
+                reinterpret_cast<float4*>(sm)[i] = __ldg(reinterpret_cast<const float4*>(qrow + d0) + i);
+#pragma unroll
+                for (int r = 0; r < RR_NR; ++r)
+                    if (src[r] >= 0)
+                        reinterpret_cast<float4*>(sm + (1 + r) * RR_ROW)[i] =
+                            __ldg(reinterpret_cast<const float4*>(pms + (size_t)src[r] * Dp + d0) + i);
+            }
+            __syncwarp();
+            if (mine) {
+                const float4* row = reinterpret_cast<const float4*>(sm + (1 + my_rank - base) * RR_ROW);
+#pragma unroll 4
+                for (int i = 0; i < n4; ++i) {
+                    const float4 qv = reinterpret_cast<const float4*>(sm)[i], sv = row[i];
+                    float df = __fsub_rn(qv.x, sv.x);
+                    acc = __fmaf_rn(df, df, acc);
+                    df = __fsub_rn(qv.y, sv.y);
+                    acc = __fmaf_rn(df, df, acc);
+                    df = __fsub_rn(qv.z, sv.z);
+                    acc = __fmaf_rn(df, df, acc);
+                    df = __fsub_rn(qv.w, sv.w);
+                    acc = __fmaf_rn(df, df, acc);
+                }
+            }
+        }
+    }
+    return acc;
+}
+// Sort <= 32 distinct keys (one per lane, lanes >= cnt hold KEY_MAX) by counting: every lane compares its key with
+// all cnt keys through broadcast shared-memory reads -- ~3 independent instructions per key instead of the 15
+// dependent shuffle stages of the bitonic network (the kernel is latency bound, not issue bound).
+__device__ __forceinline__ u64 warp_rank_sort(u64 key, int cnt, u64* sm) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    sm[lane] = key;
+    __syncwarp();
+    int r = 0;
+#pragma unroll 8
+    for (int j = 0; j < cnt; ++j) r += sm[j] < key ? 1 : 0;
+    __syncwarp();
+    if (lane < cnt) sm[32 + r] = key;
+    __syncwarp();
+    return lane < cnt ? sm[32 + lane] : KEY_MAX;
+}
+__device__ __forceinline__ unsigned ord_f32(float f) {  // order-preserving map float -> unsigned
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArgs a) {
+    __shared__ __align__(16) float sq_all[RR_WARPS][4 * RR_F4];
+    __shared__ u64 ssort[RR_WARPS][64];
+    __shared__ __align__(16) float scoop[RR_WARPS][(1 + RR_NR) * RR_ROW];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.y, qbase = (blockIdx.x * RR_WARPS + w) * RR_QPW;
+    if (qbase >= a.Nd) return;
+    const int n_pt_q = (a.Nd + KT_PTS - 1) / KT_PTS;
+    const float* pms = a.pm_s + (size_t)b * a.Ns * a.Dp;
+    float* sq = sq_all[w];
+    // software pipeline over the warp's queries: the next query's list is in flight while this one is processed
+    int c_n, ci_n;
+    float cd_n, e2_n;
+    auto load_list = [&](int q) {
+        q = min(q, a.Nd - 1);
+        const size_t qo = ((size_t)b * n_pt_q + q / KT_PTS) * KT_PTS + q % KT_PTS;
+        c_n = __ldg(a.cand_cnt + qo);
+        e2_n = __ldg(a.e2 + qo);
+        const size_t lo = ((size_t)b * n_pt_q + q / KT_PTS) * KT_CAP * KT_PTS + (size_t)lane * KT_PTS + q % KT_PTS;
+        ci_n = (int)__ldg(a.cand + lo);
+        cd_n = __ldg(a.cand_dt + lo);
+    };
+    load_list(qbase);
+#pragma unroll 1
+    for (int j = 0; j < RR_QPW; ++j) {
+        const int q = qbase + j;
+        if (q >= a.Nd) break;
+        const int c_j = c_n, ci_j = ci_n;
+        const float cd_j = cd_n, e2_j = e2_n;
+        if (j + 1 < RR_QPW) load_list(q + 1);
+        const float* qrow = a.pm_q + ((size_t)b * a.Nd + q) * a.Dp;
+        int s_out;
+        float d_out = 0.f;
+        if (c_j < 0) {
+            const u64 lk = knn_bruteforce_pm(qrow, sq, pms, a.Ns, a.Dp);
+            s_out = key_idx(lk) & 0x7fffffff;
+            d_out = key_dist(lk);
+        } else if (c_j > 32 || a.all_exact) {
+            const int qt = q / KT_PTS;
+            const u64 lk = knn_rerank(qrow, sq, pms, a.cand + ((size_t)b * n_pt_q + qt) * KT_CAP * KT_PTS + q % KT_PTS, c_j, a.Dp);
+            s_out = key_idx(lk) & 0x7fffffff;
+            d_out = key_dist(lk);
+        } else {
+            const int cnt = c_j;
+            u64 key = lane < cnt ? (((u64)ord_f32(cd_j) << 32) | (unsigned)ci_j) : KEY_MAX;
+            key = warp_rank_sort(key, cnt, ssort[w]);
+            const unsigned od = (unsigned)(key >> 32);
+            const float dts = __uint_as_float((od & 0x80000000u) ? (od & 0x7fffffffu) : ~od);
+            const int s = (int)(unsigned)(key & 0xffffffffu);
+            const float nxt = __shfl_down_sync(FULL, dts, 1);
+            const bool adj = (lane + 1 < cnt) && (nxt - dts <= e2_j);
+            const bool prev_adj = __shfl_up_sync(FULL, (int)adj, 1) != 0 && lane > 0;
+            int rs = prev_adj ? -1 : lane;  // run start marker
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, rs, o);
+                rs = lane >= o ? max(rs, v) : rs;
+            }
+            const bool need = lane < cnt && (adj || prev_adj) && rs <= LS_KNN_K - 1;
+            s_out = s;
+            if (__any_sync(FULL, need)) {
+                const float d = exact_dist_coop(need, s, qrow, pms, a.Dp, scoop[w]);
+                // final order: by run (runs are contiguous rank ranges), inside a re-sorted run by (exact d, index)
+                u64 k2 = lane < cnt ? (((u64)(unsigned)rs << 58) | ((u64)(need ? __float_as_uint(d) : 0u) << 26) | (unsigned)s) : KEY_MAX;
+                k2 = warp_rank_sort(k2, cnt, ssort[w]);
+                s_out = (int)(unsigned)(k2 & 0x3ffffffu);
+            }
+        }
+        if (lane < LS_KNN_K) {
+            const size_t o = ((size_t)b * a.Nd + q) * LS_KNN_K + lane;
+            const int64_t sv = min(s_out, a.Ns - 1);
+            a.idx_out[o] = sv;
+            if (a.idx_tap) a.idx_tap[o] = sv;
+            if (a.dist_out) a.dist_out[o] = d_out;
+        }
     }
 }
 

@@ -411,13 +411,18 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MIN_CTAS) k_knn_tc(const KnnTcA
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&sh.tmem_empty);
         }
-        // ---- stash -> global candidate list [b][qt][slot][128]
+        // ---- stash -> global candidate list [b][qt][slot][128] (index and ranking value)
         if (valid) {
-            unsigned short* cl = a.cand + ((size_t)b * a.n_pt_q + qt) * KT_CAP * KT_PTS + t;
+            const size_t base = ((size_t)b * a.n_pt_q + qt) * KT_CAP * KT_PTS + t;
             const int cnt = (int)((st_addr - st_base) / SLOT_B);
             const int n = min(cnt, KT_CAP);
-            for (int i = 0; i < n; ++i) cl[(size_t)i * KT_PTS] = (unsigned short)__float_as_uint(sh.stash[i][t].y);
+            for (int i = 0; i < n; ++i) {
+                const float2 e = sh.stash[i][t];
+                a.cand[base + (size_t)i * KT_PTS] = (unsigned short)__float_as_uint(e.y);
+                a.cand_dt[base + (size_t)i * KT_PTS] = e.x;
+            }
             a.cnt[((size_t)b * a.n_pt_q + qt) * KT_PTS + t] = (overflow || cnt > KT_CAP) ? -1 : cnt;
+            a.e2[((size_t)b * a.n_pt_q + qt) * KT_PTS + t] = e2;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -438,7 +443,7 @@ int launch_knn_pack(const float* f, int B, int D, int N, float* img, float* nrm,
 }
 
 int launch_knn_tc(const KnnTcArgs& a, int B, cudaStream_t st) {
-    LS_REQUIRE(a.img_s && a.img_q && a.nrm_s && a.nrm_q && a.cand && a.cnt, "knn_tc: null pointer");
+    LS_REQUIRE(a.img_s && a.img_q && a.nrm_s && a.nrm_q && a.cand && a.cand_dt && a.cnt && a.e2, "knn_tc: null pointer");
     LS_REQUIRE(a.Ns >= LS_KNN_K && a.Ns <= 65535 && a.Nd >= 1, "knn_tc: need 16 <= Ns <= 65535");
     const size_t smem = sizeof(KtShared) + 128;
     static bool attr_set = false;

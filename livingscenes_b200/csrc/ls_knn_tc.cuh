@@ -28,7 +28,9 @@ struct KnnTcArgs {
     int Ns, Nd, n_pt_s, n_pt_q, n_kb;
     float kappa;
     unsigned short* cand;  // [B][n_pt_q][KT_CAP][128]  candidate source indices, slot-major
+    float* cand_dt;        // [B][n_pt_q][KT_CAP][128]  their ranking values dt = |s|^2 - 2<q,s>
     int* cnt;              // [B][n_pt_q * 128]         candidates per query, -1 = overflow (brute-force it)
+    float* e2;             // [B][n_pt_q * 128]         2E of the query: two dt closer than this are "ambiguous"
 };
 
 int launch_knn_pack(const float* f, int B, int D, int N, float* img, float* nrm, float* pm, cudaStream_t st);
