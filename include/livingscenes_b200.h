@@ -154,6 +154,9 @@ LS_API int ls_vn_linear(const float* W, const float* packed, const float* X, flo
  * Both produce the same indices; kappa_scale (> 0, default 1) scales the filter's error budget (tests use a
  * huge value to force the candidate-overflow fallback). */
 LS_API int ls_set_knn_tensor_cores(int32_t on, float kappa_scale);
+/* 1 (default): ls_encoder_forward runs independent stages (FPS chain, point-level GEMM tables) on a library-owned
+ * side stream next to the kNN chain (fork/join with events; capturable).  0: everything on the caller's stream. */
+LS_API int ls_set_overlap(int32_t on);
 LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 path where packed weights exist */
 
 /* ------------------------------------------------------------------------------------------

@@ -79,6 +79,7 @@ _PROTOS = {
     "ls_vn_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p]),
     "ls_set_tensor_cores": (C.c_int, [C.c_int32]),
+    "ls_set_overlap": (C.c_int, [C.c_int32]),
     "ls_set_knn_tensor_cores": (C.c_int, [C.c_int32, C.c_float]),
     "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_knn_tc_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
@@ -169,6 +170,11 @@ def kernel_launches() -> int:
 def set_tensor_cores(on: bool) -> None:
     """Route the packed-weight GEMMs through the tcgen05 3xTF32 kernel (default) or the FP32 SIMT kernel."""
     check(lib().ls_set_tensor_cores(int(on)), "ls_set_tensor_cores")
+
+
+def set_overlap(on: bool) -> None:
+    """Side-stream overlap of independent encoder stages (default on)."""
+    check(lib().ls_set_overlap(int(on)), "ls_set_overlap")
 
 
 def set_knn_tensor_cores(on: bool, kappa_scale: float = 1.0) -> None:

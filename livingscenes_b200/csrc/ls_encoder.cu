@@ -45,6 +45,38 @@ struct ProfScope {
     }
 };
 
+// ---- fork/join helper: independent stages of one forward (FPS chain, the point-level GEMM tables) run on a
+//      library-owned side stream next to the kNN chain.  Works eagerly and under stream capture (the waits on
+//      events recorded in the capturing stream pull the side stream into the capture as a parallel branch).
+struct SideCtx {
+    int dev = -1;
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_fps = nullptr, join_tab = nullptr;
+    bool ok = false;
+};
+static thread_local SideCtx g_side;
+static bool g_overlap = true;
+
+static SideCtx* side_ctx(cudaStream_t main_stream) {
+    if (!g_overlap || g_prof_on) return nullptr;  // per-stage event timing needs the serial order
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (g_side.ok && g_side.dev == dev) return &g_side;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(main_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+        return nullptr;  // resources are only created outside a capture; this call runs serially
+    SideCtx c;
+    c.dev = dev;
+    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join_fps, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join_tab, cudaEventDisableTiming) != cudaSuccess)
+        return nullptr;
+    c.ok = true;
+    g_side = c;
+    return &g_side;
+}
+
 namespace {
 
 struct Carver {
@@ -308,6 +340,8 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             LS_CHECK_CUDA(cudaMemcpyAsync(io->x_norm, p.xn, sizeof(float) * (size_t)B * 3 * N, cudaMemcpyDeviceToDevice, st));
     }
 
+    SideCtx* sc = side_ctx(st);
+    bool fps_pending = false;
     // ---- FPS chain: all down-sampling selections depend on xyz only --------------------------
     {
         FpsArgs fa{};
@@ -325,9 +359,18 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             }
         }
         if (fa.n_levels > 0) {
-            ProfScope ps(1, -1, st);
-            rc = launch_fps(fa, B, st);
-            if (rc != LS_OK) return rc;
+            if (sc) {  // FPS only needs xyz: it runs beside layers 0..first down-sampling layer
+                LS_CHECK_CUDA(cudaEventRecord(sc->fork_ev, st));
+                LS_CHECK_CUDA(cudaStreamWaitEvent(sc->s, sc->fork_ev, 0));
+                rc = launch_fps(fa, B, sc->s);
+                if (rc != LS_OK) return rc;
+                LS_CHECK_CUDA(cudaEventRecord(sc->join_fps, sc->s));
+                fps_pending = true;
+            } else {
+                ProfScope ps(1, -1, st);
+                rc = launch_fps(fa, B, st);
+                if (rc != LS_OK) return rc;
+            }
         }
     }
 
@@ -340,6 +383,10 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         const int Ns = p.n_src[i], Nd = p.n_dst[i], Ci = L.c_in, Co = L.c_out;
         const float* dst_f = src_f;
         if (L.down_factor > 1) {
+            if (fps_pending) {
+                LS_CHECK_CUDA(cudaStreamWaitEvent(st, sc->join_fps, 0));
+                fps_pending = false;
+            }
             ProfScope ps(2, i, st);
             dim3 g((Nd + 127) / 128, Ci * 3, B);
             k_gather_points<<<g, 128, 0, st>>>(src_f, p.sel[i], Ci * 3, Ns, Nd, p.dstf);
@@ -361,6 +408,61 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         ea.out = edge_out;
         ea.idx_out = io->knn_idx[i];
         ea.idx_in = io->force_knn_idx[i];
+
+        // ---- point-level GEMM tables (layers >= 1): independent of the graph, so they run on the side stream
+        //      while the kNN chain below occupies the main stream
+        bool tables_forked = false;
+        if (i > 0) {
+            const int nb = L.attention ? 2 : 1;
+            const int r_src = 2 * nb * Co, r_dst = (2 * nb + (L.attention ? 2 : 0)) * Co;
+            cudaStream_t ts = st;
+            if (sc && ea.idx_in == nullptr) {
+                LS_CHECK_CUDA(cudaEventRecord(sc->fork_ev, st));
+                LS_CHECK_CUDA(cudaStreamWaitEvent(sc->s, sc->fork_ev, 0));
+                ts = sc->s;
+                tables_forked = true;
+            }
+            {
+                ProfScope pg(3, i, ts);
+                GemmArgs g{};
+                g.K = Ci;
+                g.ldw = Ci;
+                g.B = B;
+                g.point_major = 1;
+                g.c_out = Co;
+                // source table
+                g.W = L.w_src;
+                g.Wtc = L.w_src_tc;
+                g.R = r_src;
+                g.X = src_f;
+                g.n_per_b = 3 * Ns;
+                g.npts = Ns;
+                g.x_sb = (long long)Ci * 3 * Ns;
+                g.x_sk = 3LL * Ns;
+                g.out = p.psrc;
+                rc = launch_gemm(g, ts);
+                if (rc != LS_OK) return rc;
+                // dst table
+                g.W = L.w_dst;
+                g.Wtc = L.w_dst_tc;
+                g.R = r_dst;
+                g.X = dst_f;
+                g.n_per_b = 3 * Nd;
+                g.npts = Nd;
+                g.x_sb = (long long)Ci * 3 * Nd;
+                g.x_sk = 3LL * Nd;
+                g.out = p.pdst;
+                rc = launch_gemm(g, ts);
+                if (rc != LS_OK) return rc;
+            }
+            if (tables_forked) LS_CHECK_CUDA(cudaEventRecord(sc->join_tab, sc->s));
+            ea.psrc = p.psrc;
+            ea.pdst = p.pdst;
+            ea.row_s = r_src * 3;
+            ea.row_d = r_dst * 3;
+        }
+
+        // ---- kNN graph
         if (ea.idx_in == nullptr && Ns <= SMALL_NS) {
             ProfScope ps(4, i, st);
             dim3 gs((Nd + 7) / 8, B);
@@ -416,52 +518,11 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ea.idx_out = nullptr;
         }
         ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr);
-        if (i == 0) {
-            ea.w0 = L.w0;
+        if (tables_forked) LS_CHECK_CUDA(cudaStreamWaitEvent(st, sc->join_tab, 0));
+        {
             ProfScope ps(4, i, st);
-            rc = launch_edge(MODE_L0, ea, st);
-            if (rc != LS_OK) return rc;
-        } else {
-            const int nb = L.attention ? 2 : 1;
-            const int r_src = 2 * nb * Co, r_dst = (2 * nb + (L.attention ? 2 : 0)) * Co;
-            std::unique_ptr<ProfScope> pg(new ProfScope(3, i, st));
-            GemmArgs g{};
-            g.K = Ci;
-            g.ldw = Ci;
-            g.B = B;
-            g.point_major = 1;
-            g.c_out = Co;
-            // source table
-            g.W = L.w_src;
-            g.Wtc = L.w_src_tc;
-            g.R = r_src;
-            g.X = src_f;
-            g.n_per_b = 3 * Ns;
-            g.npts = Ns;
-            g.x_sb = (long long)Ci * 3 * Ns;
-            g.x_sk = 3LL * Ns;
-            g.out = p.psrc;
-            rc = launch_gemm(g, st);
-            if (rc != LS_OK) return rc;
-            // dst table
-            g.W = L.w_dst;
-            g.Wtc = L.w_dst_tc;
-            g.R = r_dst;
-            g.X = dst_f;
-            g.n_per_b = 3 * Nd;
-            g.npts = Nd;
-            g.x_sb = (long long)Ci * 3 * Nd;
-            g.x_sk = 3LL * Nd;
-            g.out = p.pdst;
-            rc = launch_gemm(g, st);
-            pg.reset();
-            if (rc != LS_OK) return rc;
-            ProfScope ps(4, i, st);
-            ea.psrc = p.psrc;
-            ea.pdst = p.pdst;
-            ea.row_s = r_src * 3;
-            ea.row_d = r_dst * 3;
-            rc = launch_edge(L.attention ? MODE_ATT : MODE_MEAN, ea, st);
+            if (i == 0) ea.w0 = L.w0;
+            rc = launch_edge(i == 0 ? MODE_L0 : (L.attention ? MODE_ATT : MODE_MEAN), ea, st);
             if (rc != LS_OK) return rc;
         }
         if (L.global_conv) {
@@ -502,6 +563,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         cur ^= 1;
     }
 
+    if (fps_pending) LS_CHECK_CUDA(cudaStreamWaitEvent(st, sc->join_fps, 0));
     // ---- head ------------------------------------------------------------------------------
     {
         ProfScope ps(6, -1, st);
@@ -563,6 +625,10 @@ int ls_tc_pack_weights(const float* W, int32_t R, int32_t K, int32_t ldw, float*
 int ls_set_knn_tensor_cores(int32_t on, float kappa_scale) {
     ls::g_use_knn_tc = on != 0;
     ls::g_knn_tc_kappa_scale = kappa_scale > 0.f ? kappa_scale : 1.f;
+    return LS_OK;
+}
+int ls_set_overlap(int32_t on) {
+    ls::g_overlap = on != 0;
     return LS_OK;
 }
 int ls_set_tensor_cores(int32_t on) {
