@@ -208,6 +208,18 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
 
 template <int MODE>
 int launch_edge_cpl(const EdgeArgs& a, int cpl, dim3 grid, cudaStream_t st) {
+    if (a.idx_in != nullptr) {  // graph given: phase-2-only instantiation (higher occupancy)
+        switch (cpl) {
+            case 1: k_knn_edge<MODE, 1, false><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+            case 2: k_knn_edge<MODE, 2, false><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+            case 4: k_knn_edge<MODE, 4, false><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+            case 8: k_knn_edge<MODE, 8, false><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+            case 16: k_knn_edge<MODE, 16, false><<<grid, EDGE_THREADS, 0, st>>>(a); break;
+            default: set_error("unsupported c_out/32"); return LS_ERR_INVALID;
+        }
+        LS_CHECK_LAUNCH("k_knn_edge");
+        return LS_OK;
+    }
     switch (cpl) {
         case 1: k_knn_edge<MODE, 1><<<grid, EDGE_THREADS, 0, st>>>(a); break;
         case 2: k_knn_edge<MODE, 2><<<grid, EDGE_THREADS, 0, st>>>(a); break;

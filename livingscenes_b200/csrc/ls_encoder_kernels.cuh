@@ -404,16 +404,21 @@ __device__ __noinline__ SelRet knn_select_slow(u64 k0, u64 k1, u64 k2, u64 k3, u
     return SelRet{lk, cnt};
 }
 
-template <int MODE, int CPL>
-__global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) {
+// P1 = false: phase-2-only instantiation (the graph always comes from idx_in: k_knn_rerank / k_knn_small /
+// teacher forcing) without the phase-1 tiles and queues, compiled for 3 CTAs per SM.
+#ifndef LS_P2_CTAS
+#define LS_P2_CTAS 3
+#endif
+template <int MODE, int CPL, bool P1 = true>
+__global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(const EdgeArgs a) {
     // phase-1 tiles and phase-2 scratch share one buffer
-    constexpr int TILE_FLOATS = 2 * DKC * (QT + ST);
+    constexpr int TILE_FLOATS = P1 ? 2 * DKC * (QT + ST) : 4;
     constexpr int SR_FLOATS = (MODE == MODE_ATT) ? 8 * (CPL > 4 ? CPL / 4 : 1) * LS_KNN_K * 8 : 0;
     constexpr int BUF_FLOATS = TILE_FLOATS > SR_FLOATS ? TILE_FLOATS : SR_FLOATS;
     __shared__ __align__(16) float sbuf[BUF_FLOATS];
     __shared__ int sIdx[QT][LS_KNN_K];
     __shared__ float sDist[(MODE == MODE_KNN_ONLY) ? QT : 1][LS_KNN_K];
-    __shared__ u64 sQ[8][8][QCAP];  // [warp][query][slot] candidate queues (64-bit keys)
+    __shared__ u64 sQ[P1 ? 8 : 1][P1 ? 8 : 1][P1 ? QCAP : 1];  // [warp][query][slot] candidate queues (64-bit keys)
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int b = blockIdx.y;
@@ -422,12 +427,12 @@ __global__ void __launch_bounds__(EDGE_THREADS, 2) k_knn_edge(const EdgeArgs a) 
     const int Ns = a.Ns, Nd = a.Nd, D = a.D;
     const int nq = min(qpc, Nd - q0);  // valid dst points of this CTA
 
-    if (a.idx_in != nullptr) {
+    if (!P1 || a.idx_in != nullptr) {
         for (int e = t; e < nq * LS_KNN_K; e += EDGE_THREADS) {
             int ql = e >> 4, k = e & 15;
             sIdx[ql][k] = (int)a.idx_in[((size_t)b * Nd + q0 + ql) * LS_KNN_K + k];
         }
-    } else {
+    } else if constexpr (P1) {
         // ------------------------------------------------------------------ phase 1: kNN
         float(*Qs)[DKC][QT] = reinterpret_cast<float(*)[DKC][QT]>(sbuf);
         float(*Ss)[DKC][ST] = reinterpret_cast<float(*)[DKC][ST]>(sbuf + 2 * DKC * QT);

@@ -97,6 +97,66 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
     const long long c0 = (long long)blockIdx.x * TN;
     const long long ncols = (long long)a.B * a.n_per_b;
 
+    // ---- operand staging through registers, two k-blocks ahead of the tensor core.  The global loads of
+    //      k-blocks 0 and 1 are issued before the one-time setup so that their latency overlaps it.
+    const float* wtile = wpk + (size_t)blockIdx.y * n_kb * (2 * A_STAGE_FLOATS);
+    constexpr int W_F4 = (2 * A_STAGE_FLOATS / 4) / TC_THREADS;  // float4 of the weight image per thread
+    const long long jcol = c0 + lane * 4;
+    const bool col_ok = jcol < ncols;
+    long long xoff = 0;
+    if (col_ok) {
+        const long long bb = jcol / a.n_per_b;
+        xoff = bb * a.x_sb + (jcol - bb * a.n_per_b);
+    }
+    float4 wr[2][W_F4], xr[2][4];
+    auto g_load = [&](int kb, float4* wreg, float4* xreg) {
+        // weights: contiguous 16 KB image (hi then lo)
+        const float4* src = reinterpret_cast<const float4*>(wtile + (size_t)kb * (2 * A_STAGE_FLOATS));
+#pragma unroll
+        for (int i = 0; i < W_F4; ++i) wreg[i] = __ldg(src + t + i * TC_THREADS);
+        // activations: warp w owns k-core w (4 k rows), lane owns 4 consecutive columns
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int k = kb * TKB + w * 4 + r;
+            xreg[r] = (col_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(a.X + xoff + (long long)k * a.x_sk))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto s_store = [&](int stage, const float4* wreg, const float4* v) {
+        float4* dst = reinterpret_cast<float4*>(&sh.a[stage][0][0]);
+#pragma unroll
+        for (int i = 0; i < W_F4; ++i) dst[t + i * TC_THREADS] = wreg[i];
+        // Four coalesced float4 loads gave a 4(k) x 4(n) block per thread; its transpose is four 16-byte
+        // core-matrix rows (one per column) of the canonical K-major image [kcore][ngroup][8 n][4 k].  The four
+        // stores are issued in a lane-rotated order so that each quarter-warp hits 8 distinct 16-byte bank groups.
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int i = (s4 + (lane >> 1)) & 3;  // which of the thread's 4 columns goes out in this step
+            float4 c;
+            c.x = i == 0 ? v[0].x : (i == 1 ? v[0].y : (i == 2 ? v[0].z : v[0].w));
+            c.y = i == 0 ? v[1].x : (i == 1 ? v[1].y : (i == 2 ? v[1].z : v[1].w));
+            c.z = i == 0 ? v[2].x : (i == 1 ? v[2].y : (i == 2 ? v[2].z : v[2].w));
+            c.w = i == 0 ? v[3].x : (i == 1 ? v[3].y : (i == 2 ? v[3].z : v[3].w));
+            float4 hi, lo;
+            // round to nearest TF32 (magnitude + half ulp, then clear 13 bits): lo = x - hi is exact and
+            // signed, so the tensor core's truncation of lo does not accumulate a bias over K
+            hi.x = __uint_as_float((__float_as_uint(c.x) + 0x1000u) & 0xffffe000u);
+            hi.y = __uint_as_float((__float_as_uint(c.y) + 0x1000u) & 0xffffe000u);
+            hi.z = __uint_as_float((__float_as_uint(c.z) + 0x1000u) & 0xffffe000u);
+            hi.w = __uint_as_float((__float_as_uint(c.w) + 0x1000u) & 0xffffe000u);
+            lo.x = c.x - hi.x;
+            lo.y = c.y - hi.y;
+            lo.z = c.z - hi.z;
+            lo.w = c.w - hi.w;
+            const int n = lane * 4 + i;
+            const int off = ((w * (TN / 8) + (n >> 3)) * 8 + (n & 7)) * 4;
+            *reinterpret_cast<float4*>(&sh.b[stage][0][off]) = hi;
+            *reinterpret_cast<float4*>(&sh.b[stage][1][off]) = lo;
+        }
+    };
+    g_load(0, wr[0], xr[0]);
+    if (n_kb > 1) g_load(1, wr[1], xr[1]);
+
     // ---- one-time setup: barriers, TMEM allocation (warp 0), per-column output offsets
     if (t == 0) {
         for (int s = 0; s < TC_STAGES; ++s) mbar_init(&sh.bar_empty[s], 1);
@@ -135,62 +195,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = sh.tmem_base;
 
-    const float* wtile = wpk + (size_t)blockIdx.y * n_kb * (2 * A_STAGE_FLOATS);
-
-    for (int kb = 0; kb < n_kb; ++kb) {
+    auto k_step = [&](int kb, float4* wreg, float4* xreg) {
         const int stage = kb % TC_STAGES;
         if (kb >= TC_STAGES) mbar_wait(&sh.bar_empty[stage], ((kb / TC_STAGES) - 1) & 1);
-        // weights: contiguous 16 KB image (hi then lo) -> smem
-        {
-            const float4* src = reinterpret_cast<const float4*>(wtile + (size_t)kb * (2 * A_STAGE_FLOATS));
-            float4* dst = reinterpret_cast<float4*>(&sh.a[stage][0][0]);
-#pragma unroll
-            for (int i = 0; i < (2 * A_STAGE_FLOATS / 4) / TC_THREADS; ++i) dst[t + i * TC_THREADS] = __ldg(src + t + i * TC_THREADS);
-        }
-        // activations: warp w owns k-core w (4 k rows), lane owns 4 consecutive columns.  Four coalesced
-        // float4 loads give a 4(k) x 4(n) block per thread; its transpose is four 16-byte core-matrix rows
-        // (one per column) of the canonical K-major image [kcore][ngroup][8 n][4 k].  The four stores are
-        // issued in a lane-rotated order so that each quarter-warp hits 8 distinct 16-byte bank groups.
-        {
-            const long long j = c0 + lane * 4;
-            float4 v[4];
-            bool col_ok = j < ncols;
-            long long xoff = 0;
-            if (col_ok) {
-                const long long b = j / a.n_per_b;
-                xoff = b * a.x_sb + (j - b * a.n_per_b);
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int k = kb * TKB + w * 4 + r;
-                v[r] = (col_ok && k < a.K) ? __ldg(reinterpret_cast<const float4*>(a.X + xoff + (long long)k * a.x_sk))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                const int i = (s4 + (lane >> 1)) & 3;  // which of the thread's 4 columns goes out in this step
-                float4 c;
-                c.x = i == 0 ? v[0].x : (i == 1 ? v[0].y : (i == 2 ? v[0].z : v[0].w));
-                c.y = i == 0 ? v[1].x : (i == 1 ? v[1].y : (i == 2 ? v[1].z : v[1].w));
-                c.z = i == 0 ? v[2].x : (i == 1 ? v[2].y : (i == 2 ? v[2].z : v[2].w));
-                c.w = i == 0 ? v[3].x : (i == 1 ? v[3].y : (i == 2 ? v[3].z : v[3].w));
-                float4 hi, lo;
-                // round to nearest TF32 (magnitude + half ulp, then clear 13 bits): lo = x - hi is exact and
-                // signed, so the tensor core's truncation of lo does not accumulate a bias over K
-                hi.x = __uint_as_float((__float_as_uint(c.x) + 0x1000u) & 0xffffe000u);
-                hi.y = __uint_as_float((__float_as_uint(c.y) + 0x1000u) & 0xffffe000u);
-                hi.z = __uint_as_float((__float_as_uint(c.z) + 0x1000u) & 0xffffe000u);
-                hi.w = __uint_as_float((__float_as_uint(c.w) + 0x1000u) & 0xffffe000u);
-                lo.x = c.x - hi.x;
-                lo.y = c.y - hi.y;
-                lo.z = c.z - hi.z;
-                lo.w = c.w - hi.w;
-                const int n = lane * 4 + i;
-                const int off = ((w * (TN / 8) + (n >> 3)) * 8 + (n & 7)) * 4;
-                *reinterpret_cast<float4*>(&sh.b[stage][0][off]) = hi;
-                *reinterpret_cast<float4*>(&sh.b[stage][1][off]) = lo;
-            }
-        }
+        s_store(stage, wreg, xreg);
+        if (kb + 2 < n_kb) g_load(kb + 2, wreg, xreg);  // refill this register set: in flight for two k-steps
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
         __syncthreads();
         if (t == 0) {
@@ -212,6 +221,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
             umma_commit(&sh.bar_empty[stage]);  // frees this smem stage when the MMAs have read it
             if (kb == n_kb - 1) umma_commit(&sh.bar_done);
         }
+    };
+    for (int kb = 0; kb < n_kb; kb += 2) {
+        k_step(kb, wr[0], xr[0]);
+        if (kb + 1 < n_kb) k_step(kb + 1, wr[1], xr[1]);
     }
 
     // ---- epilogue: TMEM -> registers -> global
