@@ -139,11 +139,13 @@ def knn_edge_algorithmic(g: dict):
 
 
 def measured_peaks():
+    """(HBM GB/s, source, SM MHz, TF32 dense TFLOP/s proxy = measured bf16 / 2, source)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
-    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+        return (float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0)),
+                float(d["bf16_tflops"]) / 2, "measured bf16_tflops / 2 (TF32 runs at half the bf16 rate)")
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0, 1590.0 / 2, "fallback bf16 1590 / 2"
 
 
 # --------------------------------------------------------------------------------------- CPU arm
@@ -367,10 +369,14 @@ def run_b200(args):
         ms_per_step = total_ms / args.steps
         value = n_total / (ms_per_step * 1e-3)
         e2e_val = n_total / (e2e_ms / args.steps * 1e-3)
-        # ---- roofline of the dominant fused kNN+EdgeConv launch
-        peak, peak_src, sm_max = measured_peaks()
+        # ---- roofline of the dominant kNN+EdgeConv layer.  The fused path of layer l is four launches on the
+        # same stream: k_knn_pack (features -> UMMA images), k_knn_tc (tcgen05 candidate filter), k_knn_rerank
+        # (exact fp32 re-rank) and k_knn_edge (EdgeConv + pooling); its duration is the sum of their event times.
+        peak, peak_src, sm_max, tf32_peak, tf32_src = measured_peaks()
         geo = layer_geometry(N_POINTS)
-        knn = {l: statistics.mean(v) for (n, l), v in stage_ms.items() if n == "knn_edgeconv"}
+        mean = lambda name: {l: statistics.mean(v) for (n, l), v in stage_ms.items() if n == name}
+        edge, filt, rer = mean("knn_edgeconv"), mean("knn_filter"), mean("knn_rerank")
+        knn = {l: edge[l] + filt.get(l, 0.0) + rer.get(l, 0.0) for l in edge}
         dom = max(knn, key=knn.get)
         byt, flops = knn_edge_algorithmic(geo[dom])
         dur_s = knn[dom] * 1e-3
@@ -387,9 +393,17 @@ def run_b200(args):
         all_layers = []
         for l in sorted(knn):
             b_, f_ = knn_edge_algorithmic(geo[l])
-            all_layers.append({"layer": l, "ms": round(knn[l], 4),
-                               "algorithmic_GBps": round(b_ * INST_PER_GPU / (knn[l] * 1e-3) / 1e9, 2),
-                               "reference_form_TFLOPs": round(f_ * INST_PER_GPU / (knn[l] * 1e-3) / 1e12, 2)})
+            g_ = geo[l]
+            row = {"layer": l, "ms": round(knn[l], 4), "filter_ms": round(filt.get(l, 0.0), 4),
+                   "rerank_ms": round(rer.get(l, 0.0), 4), "edgeconv_ms": round(edge[l], 4),
+                   "algorithmic_GBps": round(b_ * INST_PER_GPU / (knn[l] * 1e-3) / 1e9, 2),
+                   "reference_form_TFLOPs": round(f_ * INST_PER_GPU / (knn[l] * 1e-3) / 1e12, 2)}
+            if l in filt:
+                # tensor work of the filter: 3 TF32 MMAs (hi*hi + hi*lo + lo*hi) over padded 128-tiles
+                pad = lambda n, m: (n + m - 1) // m * m
+                tf = 3 * 2 * pad(g_["n_dst"], 128) * pad(g_["n_src"], 128) * pad(3 * g_["c_in"], 8) * INST_PER_GPU
+                row["filter_tensor_TFLOPs_incl_pack"] = round(tf / (filt[l] * 1e-3) / 1e12, 1)
+            all_layers.append(row)
         # ---- CPU baseline (bounded sample, N=1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -418,13 +432,17 @@ def run_b200(args):
             "e2e": {"value": e2e_val, "unit": "instances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": f"k_knn_edge (fused kNN+EdgeConv+pool) layer {dom}",
+            "roofline": {"bound": "hbm",
+                         "kernel": f"fused kNN+EdgeConv path of layer {dom}: k_knn_pack + k_knn_tc (tcgen05 filter) + "
+                                   "k_knn_rerank + k_knn_edge (EdgeConv + attention pool)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "launch_ms": knn[dom], "algorithmic_bytes_per_launch": byt * INST_PER_GPU,
                          "share_of_encoder": knn[dom] / enc_ms,
-                         "note": "this kernel is FP32-ALU / L2-gather bound, not HBM bound (SURVEY.md 8d); see fp32",
+                         "note": "algorithmic bytes = layer input + output features + int64 graph (SURVEY.md 8d); the path is "
+                                 "tensor/L2-gather bound, not HBM bound: see fp32 (reference-form FLOPs) and all_layers",
                          "fp32": {"achieved_TFLOPs_reference_form": flops * INST_PER_GPU / dur_s / 1e12,
                                   "peak_TFLOPs_derived": fp32_peak, "frac": flops * INST_PER_GPU / dur_s / 1e12 / fp32_peak},
+                         "tensor_peak_TFLOPs_tf32": tf32_peak, "tensor_peak_source": tf32_src,
                          "all_layers": all_layers},
             "cpu_baseline": cpu,
             "stages_ms": stages,

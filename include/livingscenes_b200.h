@@ -135,7 +135,7 @@ LS_API int ls_encoder_forward(const ls_encoder_desc* desc, const ls_encoder_io* 
  * stage with CUDA events on the launching stream; after the caller has synchronised the stream,
  * ls_profile_read returns (stage, layer, milliseconds) of the LAST forward call.
  * stage: 0 normalize, 1 fps, 2 gather dst, 3 point-level GEMM tables, 4 fused kNN+EdgeConv+pool,
- *        5 global-context conv, 6 head, 7 tensor-core kNN filter (pack + filter).  ls_kernel_launches counts every kernel this library launched. */
+ *        5 global-context conv, 6 head, 7 tensor-core kNN filter (pack + filter), 8 kNN re-rank.  ls_kernel_launches counts every kernel this library launched. */
 LS_API int ls_profile_enable(int32_t on);
 LS_API int ls_profile_read(int32_t* stage, int32_t* layer, float* ms, int32_t max_entries, int32_t* n_entries);
 LS_API int64_t ls_kernel_launches(void);

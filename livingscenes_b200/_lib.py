@@ -148,7 +148,7 @@ def require_cuda(t: torch.Tensor, name: str) -> None:
             "(the CPU restatement lives in oracle/ and is test infrastructure only).")
 
 
-STAGE_NAMES = ("normalize", "fps", "gather", "gemm_tables", "knn_edgeconv", "global_conv", "head", "knn_filter")
+STAGE_NAMES = ("normalize", "fps", "gather", "gemm_tables", "knn_edgeconv", "global_conv", "head", "knn_filter", "knn_rerank")
 
 
 def profile_enable(on: bool) -> None:

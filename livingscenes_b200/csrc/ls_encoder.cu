@@ -2,6 +2,7 @@
 //   ls_encoder_forward   VecDGCNN_att.forward / Shape_Prior.encode
 //   ls_knn, ls_fps       the pytorch3d boundary as stand-alone ops
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <memory>
 #include <vector>
@@ -232,11 +233,26 @@ int launch_edge_cpl(const EdgeArgs& a, int cpl, dim3 grid, cudaStream_t st) {
     return LS_OK;
 }
 
-// dst points per CTA: as many as the tile holds, fewer when the grid would not fill the GPU twice
-int pick_qpc(int B, int Nd, bool phase2_only) {
+// dst points per CTA: as many as the tile holds, fewer when the grid would not fill the GPU twice.
+// Phase-2-only launches gather rows of the instance's point-level tables (table_bytes per instance); the CTAs of
+// one instance are adjacent in the grid, so the number of instances in flight is (resident CTAs) / (CTAs per
+// instance).  Keeping that working set inside L2 (126 MB) turns the repeated row gathers into L2 hits -- with 64
+// points per CTA layers 2-4 had 55-220 instances (0.3-1.2 GB of tables) in flight and re-read every row from HBM.
+int pick_qpc(int B, int Nd, bool phase2_only, int Co = 0, size_t table_bytes = 0) {
     int qpc = QT;
     const int floor_q = phase2_only ? 8 : 16;
     while (qpc > floor_q && (long long)B * ((Nd + qpc - 1) / qpc) < 4 * 148) qpc >>= 1;
+    if (phase2_only && table_bytes > 0) {
+        const int lpp = std::max(1, std::min(Co / 4, 32));   // lanes per point in phase 2
+        const int min_q = std::max(8, 8 * (32 / lpp));        // one pass of the CTA's 8 warps
+        const long long slots = 148LL * LS_P2_CTAS, budget = 64LL << 20;
+        while (qpc > min_q) {
+            const long long per_inst = (Nd + qpc - 1) / qpc;
+            const long long in_flight = (slots + per_inst - 1) / per_inst;
+            if (in_flight * (long long)table_bytes <= budget) break;
+            qpc >>= 1;
+        }
+    }
     return qpc;
 }
 
@@ -484,7 +500,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         }
         if (ea.idx_in == nullptr && g_use_knn_tc) {
             // tensor-core candidate filter + exact re-rank instead of the brute-force phase 1
-            ProfScope ps(7, i, st);
+            std::unique_ptr<ProfScope> ps(new ProfScope(7, i, st));
             const int D = Ci * 3;
             rc = launch_knn_pack(src_f, B, D, Ns, p.kimg_s, p.knrm_s, p.kpm_s, st);
             if (rc != LS_OK) return rc;
@@ -515,6 +531,8 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ka.e2 = p.ke2;
             rc = launch_knn_tc(ka, B, st);
             if (rc != LS_OK) return rc;
+            ps.reset();
+            ps.reset(new ProfScope(8, i, st));
             ra.cand = p.kcand;
             ra.cand_dt = p.kcand_dt;
             ra.cand_cnt = p.kcnt;
@@ -529,7 +547,8 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ea.idx_in = p.kidx;
             ea.idx_out = nullptr;
         }
-        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr);
+        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr, Co,
+                          i > 0 ? sizeof(float) * ((size_t)ea.row_s * Ns + (size_t)ea.row_d * Nd) : 0);
         if (tables_forked) LS_CHECK_CUDA(cudaStreamWaitEvent(st, sc->join_tab, 0));
         {
             ProfScope ps(4, i, st);
