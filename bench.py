@@ -229,10 +229,13 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner to STDOUT (fd 1) when the first communicator is created: point fd 1 at
+        # stderr until the JSON line is due, so that stdout carries exactly one line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
 
@@ -449,10 +452,21 @@ def run_b200(args):
             "eager_ms_per_step": eager_ms / args.steps,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
         }
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line))
     if world > 1:
+        # The captured step holds NCCL work: drop the graph before tearing the communicator down, and leave with a
+        # hard exit once every rank is past the barrier -- destroy_process_group() next to a live captured
+        # collective was seen to hang the job after the JSON line had been printed.
+        sys.stdout.flush()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        del graph, static_out
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
