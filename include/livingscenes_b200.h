@@ -184,6 +184,12 @@ LS_API int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t
  * xyz [B,3,N] -> idx [B,n_out] int64, optional out_xyz [B,3,n_out]. */
 LS_API int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz,
            void* stream);
+/* ls_fps with an optional per-instance first index (start_idx [B] int64 on the device, NULL = 0: pytorch3d's
+ * random_start_point=True picks it at random, model_utils.py:202-205) and support for large clouds: N > 8192
+ * (scene instances of up to ~10^5 points) runs from a caller-provided scratch of ls_fps_workspace_bytes. */
+LS_API int ls_fps_workspace_bytes(int32_t B, int32_t N, size_t* bytes);
+LS_API int ls_fps_ex(const float* xyz, int32_t B, int32_t N, int32_t n_out, const int64_t* start_idx, int64_t* idx,
+              float* out_xyz, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Matching: lib_more/matcher_new.py

@@ -791,10 +791,25 @@ int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int
     return LS_OK;
 }
 
-int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz,
-           void* stream) {
+int ls_fps_workspace_bytes(int32_t B, int32_t N, size_t* bytes) {
+    LS_REQUIRE(bytes && B >= 1 && N >= 1, "bad arguments");
+    *bytes = N > 8192 ? (size_t)B * N * sizeof(float4) : 0;
+    return LS_OK;
+}
+
+int ls_fps_ex(const float* xyz, int32_t B, int32_t N, int32_t n_out, const int64_t* start_idx, int64_t* idx,
+              float* out_xyz, void* workspace, size_t workspace_bytes, void* stream) {
     LS_REQUIRE(xyz && idx, "null pointer");
-    LS_REQUIRE(B >= 1, "bad batch");
+    LS_REQUIRE(B >= 1 && N >= 1 && n_out >= 1 && n_out <= N, "fps: need 1 <= n_out <= N");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (N > 8192) {
+        LS_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)B * N * sizeof(float4),
+                   "fps: N > 8192 needs the scratch of ls_fps_workspace_bytes");
+        LS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "fps: workspace must be 16-byte aligned");
+        k_fps_large<<<B, 1024, 0, st>>>(xyz, N, n_out, start_idx, static_cast<float4*>(workspace), idx, out_xyz);
+        LS_CHECK_LAUNCH("k_fps_large");
+        return LS_OK;
+    }
     FpsArgs fa{};
     fa.xyz = xyz;
     fa.N = N;
@@ -802,7 +817,13 @@ int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, 
     fa.n_out[0] = n_out;
     fa.sel64[0] = idx;
     fa.out_xyz = out_xyz;
-    return launch_fps(fa, B, static_cast<cudaStream_t>(stream));
+    fa.start = start_idx;
+    return launch_fps(fa, B, st);
+}
+
+int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz, void* stream) {
+    LS_REQUIRE(N <= 8192, "ls_fps: N > 8192 needs ls_fps_ex with a workspace");
+    return ls_fps_ex(xyz, B, N, n_out, nullptr, idx, out_xyz, nullptr, 0, stream);
 }
 
 }  // extern "C"

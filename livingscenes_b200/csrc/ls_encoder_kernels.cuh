@@ -150,6 +150,7 @@ struct FpsArgs {
     int64_t* sel64[FPS_MAX_LEVELS];    // optional [B][n_out] int64 (API tap)
     const int64_t* force[FPS_MAX_LEVELS];  // optional forced selections (teacher forcing)
     float* out_xyz;                      // optional [B][3][n_out[last]]
+    const int64_t* start;                // optional [B] first selected index of level 0 (default 0)
 };
 
 template <int PPT>
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
                 pz[p] = ok ? cur[2 * n_cur + i] : 0.f;
                 md[p] = ok ? FLT_MAX : -1.f;  // padding can never win the arg-max
             }
-            int last = 0;
-            if (t == 0) ssel[0] = 0;
+            int last = (lv == 0 && a.start) ? (int)a.start[b] : 0;
+            if (t == 0) ssel[0] = last;
             for (int j = 1; j < n_out; ++j) {
                 const float lx = cur[last], ly = cur[n_cur + last], lz = cur[2 * n_cur + last];
                 float bv = -2.f;
@@ -251,6 +252,83 @@ __global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
     if (a.out_xyz) {
         float* o = a.out_xyz + (size_t)b * 3 * n_cur;
         for (int i = t; i < 3 * n_cur; i += T) o[i] = cur[i];
+    }
+}
+
+// Large clouds (N > 8192: scene-level instances of up to ~10^5 points, model_utils.py:199-205): one CTA per
+// instance, the running min-distance lives in a caller-provided scratch as float4 {x,y,z,min_d} per point (L2
+// resident: one 16-byte load and one 4-byte store per point and step), same arithmetic and tie rule as k_fps.
+__global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xyz, int N, int n_out,
+                                                    const int64_t* __restrict__ start, float4* __restrict__ scr,
+                                                    int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+    __shared__ float wb_v[2][32];
+    __shared__ int wb_i[2][32];
+    const int T = blockDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
+    const float* xb = xyz + (size_t)b * 3 * N;
+    float4* sb = scr + (size_t)b * N;
+    for (int i = t; i < N; i += T) sb[i] = make_float4(xb[i], xb[N + i], xb[2 * N + i], FLT_MAX);
+    int last = start ? (int)start[b] : 0;
+    if (t == 0) {
+        sel64[(size_t)b * n_out] = last;
+        if (out_xyz) {
+            float* o = out_xyz + (size_t)b * 3 * n_out;
+            o[0] = xb[last];
+            o[n_out] = xb[N + last];
+            o[2 * n_out] = xb[2 * N + last];
+        }
+    }
+    __syncthreads();
+    for (int j = 1; j < n_out; ++j) {
+        const float lx = __ldg(xb + last), ly = __ldg(xb + N + last), lz = __ldg(xb + 2 * N + last);
+        float bv = -2.f;
+        int bi = 0x7fffffff;
+        for (int i = t; i < N; i += T) {
+            const float4 p = sb[i];
+            const float dx = p.x - lx, dy = p.y - ly, dz = p.z - lz;
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float m = fminf(p.w, d);
+            sb[i].w = m;
+            if (m > bv) {  // strict: lowest index within the thread wins
+                bv = m;
+                bi = i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(FULL, bv, o);
+            const int i2 = __shfl_xor_sync(FULL, bi, o);
+            if (v2 > bv || (v2 == bv && i2 < bi)) {
+                bv = v2;
+                bi = i2;
+            }
+        }
+        const int par = j & 1;
+        if (lane == 0) {
+            wb_v[par][w] = bv;
+            wb_i[par][w] = bi;
+        }
+        __syncthreads();
+        bv = lane < nw ? wb_v[par][lane] : -2.f;
+        bi = lane < nw ? wb_i[par][lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(FULL, bv, o);
+            const int i2 = __shfl_xor_sync(FULL, bi, o);
+            if (v2 > bv || (v2 == bv && i2 < bi)) {
+                bv = v2;
+                bi = i2;
+            }
+        }
+        last = bi;
+        if (t == 0) {
+            sel64[(size_t)b * n_out + j] = last;
+            if (out_xyz) {
+                float* o = out_xyz + (size_t)b * 3 * n_out + j;
+                o[0] = xb[last];
+                o[n_out] = xb[N + last];
+                o[2 * n_out] = xb[2 * N + last];
+            }
+        }
     }
 }
 

@@ -129,20 +129,29 @@ class Shape_Prior(nn.Module):
 
     def encode_fps(self, batch_pc, batch_mask, n_fps=1):
         """batch_pc [B,3,Nmax], batch_mask [B,1,Nmax] bool (model_utils.py:199-215): per instance keep the
-        valid points, FPS to ``field_input_n`` (start index 0), encode.  The FPS runs per instance
-        (ragged sizes) but the encoder runs ONCE on the whole batch instead of B times with B=1."""
+        valid points, FPS to ``field_input_n`` (start index 0; ``n_fps`` > 1: that many random start indices per
+        instance, codes averaged), encode.  The FPS runs per instance (ragged sizes, up to ~10^5 points) but the
+        encoder runs ONCE on the whole batch instead of B times with B = n_fps."""
         assert batch_pc.shape[-1] == batch_mask.shape[-1], "point cloud and mask must have same length!"
-        if n_fps != 1:
-            raise NotImplementedError("n_fps > 1 uses random FPS restarts in the reference; only the "
-                                      "deterministic n_fps == 1 path used by the evals is built")
         from .ops import farthest_point_sample
 
+        n_fps = int(n_fps)
+        assert n_fps >= 1
         pcs = []
         for pc, mask in zip(batch_pc, batch_mask):
             valid = pc[:, mask.reshape(-1)].unsqueeze(0).contiguous()  # [1,3,Nv]
-            _, sub = farthest_point_sample(valid, self.field_input_n)
+            if n_fps == 1:
+                _, sub = farthest_point_sample(valid, self.field_input_n)
+            else:  # random restarts (model_utils.py:202,205): first index drawn per restart, codes averaged below
+                start = torch.randint(0, valid.shape[-1], (n_fps,), dtype=torch.int64)
+                _, sub = farthest_point_sample(valid.expand(n_fps, -1, -1).contiguous(), self.field_input_n, start)
             pcs.append(sub)
-        return self.encode(torch.cat(pcs, 0))
+        code = self.encode(torch.cat(pcs, 0))
+        if n_fps == 1:
+            return code
+        # average the embeddings of the restarts of each instance (model_utils.py:209)
+        B = len(pcs)
+        return {k: v.reshape(B, n_fps, *v.shape[1:]).mean(1) for k, v in code.items()}
 
     def forward(self, x):
         raise NotImplementedError()

@@ -79,26 +79,38 @@ def knn_graph_cm_tc(query_cm: torch.Tensor, source_cm: torch.Tensor):
 
 
 @torch.no_grad()
-def farthest_point_sample(xyz_cm: torch.Tensor, n_out: int):
-    """xyz [B,3,N] (channel-major) -> (idx [B,n_out] int64, sampled xyz [B,3,n_out]); start index 0."""
+def farthest_point_sample(xyz_cm: torch.Tensor, n_out: int, start_idx: torch.Tensor = None):
+    """xyz [B,3,N] (channel-major) -> (idx [B,n_out] int64, sampled xyz [B,3,n_out]).  ``start_idx`` [B] int64
+    chooses the first selected point per instance (default 0, pytorch3d's random_start_point=False)."""
     _lib.require_cuda(xyz_cm, "xyz")
     B, three, N = xyz_cm.shape
     assert three == 3
     x = xyz_cm.detach().float().contiguous()
     idx = torch.empty(B, n_out, dtype=torch.int64, device=x.device)
     out = torch.empty(B, 3, n_out, dtype=torch.float32, device=x.device)
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.lib().ls_fps_workspace_bytes(B, N, C.byref(nbytes)), "ls_fps_workspace_bytes")
+    ws = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=x.device)
+    st = None
+    if start_idx is not None:
+        st = start_idx.to(device=x.device, dtype=torch.int64).contiguous()
+        assert st.shape == (B,) and int(st.min()) >= 0 and int(st.max()) < N
     with torch.cuda.device(x.device):
-        rc = _lib.lib().ls_fps(x.data_ptr(), B, N, n_out, idx.data_ptr(), out.data_ptr(), _lib.stream_ptr(x.device))
-        _lib.check(rc, "ls_fps")
+        rc = _lib.lib().ls_fps_ex(x.data_ptr(), B, N, n_out, _lib.ptr(st), idx.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                  ws.numel(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "ls_fps_ex")
         _lib.launch_count += 1
     return idx, out
 
 
 def sample_farthest_points(points: torch.Tensor, K: int = 50, random_start_point: bool = False):
-    """pytorch3d signature: points [B,P,3] -> (pts [B,K,3], idx [B,K])."""
+    """pytorch3d signature: points [B,P,3] -> (pts [B,K,3], idx [B,K]).  ``random_start_point`` draws the first
+    index per instance from torch's global RNG (pytorch3d draws it from its own RNG: the sequences differ, the
+    distribution does not)."""
+    start = None
     if random_start_point:
-        raise NotImplementedError("random_start_point is not built (the evals use n_init = 1, start index 0)")
-    idx, out = farthest_point_sample(points.transpose(1, 2), K)
+        start = torch.randint(0, points.shape[1], (points.shape[0],), dtype=torch.int64)
+    idx, out = farthest_point_sample(points.transpose(1, 2), K, start)
     return out.transpose(1, 2).to(points.dtype), idx
 
 

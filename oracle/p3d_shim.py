@@ -90,8 +90,10 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm: int = 2, K: int = 1,
     return dists.to(dev), idx.to(dev), nn
 
 
-def sample_farthest_points(points, lengths=None, K: int = 50, random_start_point: bool = False):
-    assert lengths is None and not random_start_point, "oracle shim: deterministic start only"
+def sample_farthest_points(points, lengths=None, K: int = 50, random_start_point: bool = False, start_idx=None):
+    """``start_idx`` [B] (oracle extension): the first selected index per cloud -- what pytorch3d draws at random
+    when random_start_point=True (sample_farthest_points.py); default 0."""
+    assert lengths is None and not random_start_point, "oracle shim: pass start_idx instead of random_start_point"
     assert points.dim() == 3 and points.shape[2] == 3
     B, P, _ = points.shape
     assert K <= P
@@ -99,7 +101,8 @@ def sample_farthest_points(points, lengths=None, K: int = 50, random_start_point
     px, py, pz = x[..., 0].contiguous(), x[..., 1].contiguous(), x[..., 2].contiguous()
     idx = torch.zeros(B, K, dtype=torch.int64)
     min_d = torch.full((B, P), float("inf"), dtype=torch.float32)
-    last = torch.zeros(B, dtype=torch.int64)
+    last = torch.zeros(B, dtype=torch.int64) if start_idx is None else start_idx.detach().cpu().to(torch.int64).clone()
+    idx[:, 0] = last
     ar = torch.arange(B)
     for j in range(1, K):
         dx = px - px[ar, last][:, None]

@@ -106,3 +106,72 @@ def encoder_emulated(enc, x, knn_idx, fps_idx):
     if enc.center_pred_scale:
         center = center * enc.scale_factor
     return center.unsqueeze(1), scale, z_so3, z_inv, feats
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU emulation of the tensor-core kNN path (csrc/ls_knn_tc.cu + k_knn_rerank): ranking value from a 3xTF32
+# product, threshold from group minima, candidate set, hybrid re-rank (exact distances for ambiguous runs only).
+def _tf32_rn(x):
+    import numpy as np
+    u = x.view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _tf32_trunc(x):
+    import numpy as np
+    return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tc_knn_emulated(q, s, K=16, group_cols=256, kappa_scale=1.0):
+    """q [D,Nq], s [D,Ns] float32 numpy -> (idx [Nq,K] int64, stats).  Mirrors the kernels' decisions; the exact
+    distance is the sequential fp32 FMA form of the brute-force kernel."""
+    import numpy as np
+
+    D, Nq = q.shape
+    Ns = s.shape[1]
+    ns = np.zeros(Ns, np.float32)
+    nq = np.zeros(Nq, np.float32)
+    for d in range(D):
+        ns = (s[d] * s[d] + ns).astype(np.float32)
+        nq = (q[d] * q[d] + nq).astype(np.float32)
+    sh, qh = _tf32_rn(s), _tf32_rn(q)
+    sl, ql = _tf32_trunc((s - sh).astype(np.float32)), _tf32_trunc((q - qh).astype(np.float32))
+    f64 = np.float64
+    dot = (qh.T.astype(f64) @ sh.astype(f64) + qh.T.astype(f64) @ sl.astype(f64) + ql.T.astype(f64) @ sh.astype(f64))
+    dt = (ns[None, :] - 2 * dot.astype(np.float32)).astype(np.float32)
+    kappa = kappa_scale * (2 * D * 2.0 ** -23 + 2.0 ** -16)
+    e2 = (2 * kappa * (nq + ns.max())).astype(np.float32)
+
+    def exact(qi, si):  # sequential fp32 FMA chain (float64 product of float32 factors rounds like an FMA)
+        acc = np.float32(0)
+        for d in range(D):
+            df = np.float32(q[d, qi] - s[d, si])
+            acc = np.float32(f64(df) * f64(df) + f64(acc))
+        return acc
+
+    idx = np.zeros((Nq, K), np.int64)
+    n_cand, n_exact = [], []
+    for i in range(Nq):
+        m = np.full(32, np.inf, np.float32)
+        stash = []
+        for g0 in range(0, Ns, group_cols):
+            cols = np.arange(g0, min(g0 + group_cols, Ns))
+            np.minimum.at(m, cols % 32, dt[i, cols])
+            thr = np.sort(m)[15] + e2[i]
+            stash = [c for c in stash if dt[i, c] <= thr] + [c for c in cols if dt[i, c] <= thr]
+        cand = sorted(stash, key=lambda c: (dt[i, c], c))
+        n_cand.append(len(cand))
+        # runs of candidates chained by gaps <= 2E that reach into the first K ranks get exact distances
+        run_start, need = [], []
+        for r, c in enumerate(cand):
+            adj_prev = r > 0 and np.float32(dt[i, c] - dt[i, cand[r - 1]]) <= e2[i]
+            run_start.append(run_start[-1] if adj_prev else r)
+        for r, c in enumerate(cand):
+            adj_next = r + 1 < len(cand) and np.float32(dt[i, cand[r + 1]] - dt[i, c]) <= e2[i]
+            adj_prev = run_start[r] != r
+            need.append((adj_prev or adj_next) and run_start[r] <= K - 1)
+        n_exact.append(sum(need))
+        order = sorted(range(len(cand)), key=lambda r: (run_start[r], exact(i, cand[r]) if need[r] else np.float32(0), cand[r]))
+        idx[i] = [cand[r] for r in order[:K]]
+    return idx, {"candidates_mean": float(np.mean(n_cand)), "candidates_max": int(max(n_cand)),
+                 "exact_per_query_mean": float(np.mean(n_exact))}

@@ -201,6 +201,120 @@ def test_encoder_knn_tc_equals_brute_force(tag, B, N, dev, oracle_R):
         assert torch.equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("kappa_scale", [0.25, 8.0, 64.0])
+def test_knn_tc_error_budget_does_not_change_the_graph(kappa_scale, dev, oracle_R):
+    """The filter's error budget only decides how many candidates are re-ranked and how many of them need exact
+    distances (wider budget -> longer ambiguous runs): the graph must not depend on it.  0.25 is still ~10x the
+    measured tensor-core error; 64 makes most neighbouring candidates 'ambiguous'."""
+    from livingscenes_b200 import _lib
+    from livingscenes_b200.ops import knn_graph_cm, knn_graph_cm_tc
+
+    sd = state_dict_for("random")
+    tr = {}
+    with torch.no_grad():
+        oracle_R.encode(sd, oracle_R.synth_instances(2, 1024, 77), trace=tr)
+    for i in (0, 1, 3):
+        sf, df = tr["src_f"][i], tr["dst_f"][i]
+        B, C, _, Ns = sf.shape
+        q, s = df.reshape(B, C * 3, -1).to(dev), sf.reshape(B, C * 3, Ns).to(dev)
+        idx_e, d_e = knn_graph_cm(q, s)
+        try:
+            _lib.set_knn_tensor_cores(True, kappa_scale)
+            idx_t, d_t, nc = knn_graph_cm_tc(q, s)
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_knn_tensor_cores(True, 1.0)
+        assert torch.equal(idx_e, idx_t) and torch.equal(d_e, d_t), f"layer {i}, kappa_scale {kappa_scale}"
+
+
+def test_encoder_overlap_and_budget_invariance(dev, oracle_R):
+    """Side-stream overlap on/off and a wide error budget (hybrid re-rank computes exact distances for most
+    candidates) give bit-identical graphs and embeddings; also under CUDA-graph capture + replay."""
+    from livingscenes_b200 import _lib
+
+    enc = _model("random", dev).encoder
+    x = oracle_R.synth_instances(6, 1024, 4242).to(dev)
+    ref = enc.run(x, normalize=True, taps=True)
+    torch.cuda.synchronize()
+    try:
+        for overlap, ks in ((False, 1.0), (True, 32.0), (False, 32.0)):
+            _lib.set_overlap(overlap)
+            _lib.set_knn_tensor_cores(True, ks)
+            r = enc.run(x, normalize=True, taps=True)
+            torch.cuda.synchronize()
+            for i, (ia, ib) in enumerate(zip(ref["knn_idx"], r["knn_idx"])):
+                assert torch.equal(ia, ib), f"layer {i} overlap={overlap} kappa_scale={ks}"
+            for k in ("z_so3", "z_inv", "scale", "center"):
+                assert torch.equal(ref[k], r[k]), k
+    finally:
+        _lib.set_overlap(True)
+        _lib.set_knn_tensor_cores(True, 1.0)
+    # capture + replay with the side stream forked inside the capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        enc.run(x, normalize=True)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = enc.run(x, normalize=True)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    for k in ("z_so3", "z_inv", "scale", "center"):
+        assert torch.equal(ref[k], out[k]), f"graph replay: {k}"
+
+
+@pytest.mark.parametrize("N,n_out", [(20000, 1024), (9000, 300), (4000, 1024)])
+def test_fps_start_index_and_large_clouds(N, n_out, dev):
+    """ls_fps_ex: caller-chosen first index (random_start_point) and the large-cloud kernel (N > 8192) select
+    exactly the oracle's points."""
+    from livingscenes_b200.ops import farthest_point_sample
+    from oracle.p3d_shim import sample_farthest_points as ref_fps
+
+    g = torch.Generator().manual_seed(N)
+    pts = torch.randn(2, N, 3, generator=g) * torch.tensor([1.0, 0.5, 2.0])
+    start = torch.tensor([5, N - 3])
+    _, ridx = ref_fps(pts, K=n_out, start_idx=start)
+    idx, out = farthest_point_sample(pts.transpose(1, 2).to(dev), n_out, start.to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu(), ridx)
+    assert torch.equal(out.cpu(), torch.gather(pts, 1, ridx[..., None].expand(-1, -1, 3)).transpose(1, 2))
+
+
+def test_encode_fps_random_restarts(dev, oracle_R):
+    """Shape_Prior.encode_fps(n_fps=3) (model_utils.py:199-215): ragged masked instances, three FPS restarts each
+    with random first indices, codes averaged -- against the oracle fed the same start indices."""
+    from oracle.p3d_shim import sample_farthest_points as ref_fps
+
+    sd = state_dict_for("random")
+    model = _model("random", dev)
+    g = torch.Generator().manual_seed(9)
+    B, Nmax, n_fps = 2, 3000, 3
+    pc = torch.randn(B, 3, Nmax, generator=g) * 0.3
+    mask = torch.zeros(B, 1, Nmax, dtype=torch.bool)
+    mask[0, 0, :2500] = True
+    mask[1, 0, 200:1700] = True
+    torch.manual_seed(123)
+    out = model.encode_fps(pc.to(dev), mask.to(dev), n_fps=n_fps)
+    torch.cuda.synchronize()
+    torch.manual_seed(123)
+    ref = {k: [] for k in ("z_so3", "z_inv", "s", "t")}
+    with torch.no_grad():
+        for b in range(B):
+            valid = pc[b][:, mask[b, 0]]
+            start = torch.randint(0, valid.shape[-1], (n_fps,), dtype=torch.int64)
+            sub, _ = ref_fps(valid.T[None].expand(n_fps, -1, -1).contiguous(), K=model.field_input_n, start_idx=start)
+            code = oracle_R.encode(sd, sub.transpose(1, 2).contiguous())
+            for k in ref:
+                ref[k].append(code[k].mean(0, keepdim=True))
+    for k in ref:
+        r = torch.cat(ref[k], 0)
+        assert out[k].shape == r.shape, k
+        assert relerr(out[k].cpu(), r) < TOL, k
+
+
 @pytest.mark.parametrize("N,n_out", [(1024, 512), (2048, 1024), (1000, 77), (5000, 1024), (16, 16)])
 def test_fps_bit_exact(N, n_out, dev, oracle_R):
     from livingscenes_b200.ops import farthest_point_sample
