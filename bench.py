@@ -319,7 +319,6 @@ def run_b200(args):
         total_ms += ev[k][0].elapsed_time(ev[k][1])
     barrier()
     wall_ms = (time.perf_counter() - wall0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- the same K steps launched eagerly with per-stage CUDA events (ls_profile_*): kernel
     # durations for the roofline, and the launch count of one step (a graph replay issues the same kernels)
@@ -359,6 +358,7 @@ def run_b200(args):
         b.synchronize()
         e2e_ms += a.elapsed_time(b)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None  # sampled over all three timed regions (value, per-stage, e2e)
     h2d = host_sets[0].numel() * 4
     d2h = h_m.numel() * 8 + h_R.numel() * 4 + h_t.numel() * 4
 
