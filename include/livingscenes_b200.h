@@ -221,6 +221,15 @@ LS_API int ls_kabsch_from_codes(const float* z_so3_a, const float* t_a, const fl
                          const int64_t* match, int32_t n_pairs, int32_t c_dim, float* R, float* t,
                          float* res, void* stream);
 
+/* ICP refinement after the pose fit (more_solver.py:182-187: pytorch3d.ops.iterative_closest_point(pc1, pc2,
+ * init_transform=SimilarityTransform(R^T, t, 1)), estimate_scale=False, allow_reflection=False).  Row-vector
+ * convention like pytorch3d: Xt = X R + T.  X [B,N,3] (N <= 4096), Y [B,M,3] (M <= 12288), R0 [B,3,3] / T0 [B,3]
+ * optional initial transform; outputs R [B,3,3], T [B,3], rmse [B], n_iter [B] (iterations executed, negated when
+ * the relative-rmse test never fired within max_iterations), optional Xt [B,N,3].  One CTA per pair. */
+LS_API int ls_icp(const float* X, const float* Y, int32_t B, int32_t N, int32_t M, const float* R0, const float* T0,
+           int32_t max_iterations, float relative_rmse_thr, float* R, float* T, float* rmse, int32_t* n_iter, float* Xt,
+           void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * SDF query: FieldWrapper.forward (model_utils.py:230-263, inner_deepsdf branch) +
  * DeepSDF_Decoder.forward (lib_shape_prior/core/lib/implicit_func/deepsdf_decoder.py:78-123)

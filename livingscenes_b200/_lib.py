@@ -98,6 +98,8 @@ _PROTOS = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_kabsch_from_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_icp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_sdf_workspace_bytes": (C.c_int, [C.POINTER(DecoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "ls_sdf_decode": (C.c_int, [C.POINTER(DecoderDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

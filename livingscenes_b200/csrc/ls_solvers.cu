@@ -404,6 +404,183 @@ __global__ void __launch_bounds__(128) k_kabsch(const KabschArgs a) {
     }
 }
 
+// ============================================================================================
+// ICP refinement of the pose fit (more_solver.py:182-187 -> pytorch3d.ops.iterative_closest_point with
+// init_transform, estimate_scale=False, allow_reflection=False; restated in oracle/p3d_shim.py):
+//   Xt = s X R + T (row vectors);  loop: nn = 1-NN of Xt in Y (direct-form fp32 distance, lowest index on ties);
+//   (R, T) = corresponding_points_alignment(X, nn): means, XYcov = Xc^T Yc / N, SVD, R = U diag(1,1,det(U V^T)) V^T,
+//   T = Ymu - Xmu R;  Xt = X R + T;  rmse = sqrt(mean |Xt - nn|^2);  stop when (prev - rmse) / prev <= thr.
+// One CTA per pair: Y as float4 in shared memory (broadcast reads), every thread owns N/blockDim points of X.
+// ============================================================================================
+constexpr int ICP_THREADS = 512, ICP_PPT = 8;  // N <= 4096
+struct IcpArgs {
+    const float* X;   // [B][N][3]
+    const float* Y;   // [B][M][3]
+    const float* R0;  // optional [B][3][3] row-vector convention (Xt = X R + T)
+    const float* T0;  // optional [B][3]
+    int N, M, max_iter;
+    float rel_thr;
+    float *R, *T, *rmse, *Xt;  // Xt optional [B][N][3]
+    int32_t* n_iter;           // iterations executed; negated when the convergence test never fired
+};
+
+__device__ __forceinline__ void icp_block_sum(float* v, int n, float* red, float* out) {
+    // sums v[0..n) over the block (n <= 9); result broadcast through out[0..n)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = 0; i < n; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0)
+        for (int i = 0; i < n; ++i) red[w * 9 + i] = v[i];
+    __syncthreads();
+    if (threadIdx.x < n) {
+        float s = 0.f;
+        for (int k = 0; k < nw; ++k) s += red[k * 9 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(ICP_THREADS) k_icp(const IcpArgs a) {
+    extern __shared__ float4 sY[];  // [M]
+    __shared__ float red[(ICP_THREADS / 32) * 9];
+    __shared__ float bc[12];  // broadcast slot: sums, then R (9) + T (3)
+    __shared__ int s_stop;
+    const int b = blockIdx.x, t = threadIdx.x, N = a.N, M = a.M;
+    const float* Xb = a.X + (size_t)b * N * 3;
+    const float* Yb = a.Y + (size_t)b * M * 3;
+    for (int j = t; j < M; j += ICP_THREADS) sY[j] = make_float4(Yb[j * 3], Yb[j * 3 + 1], Yb[j * 3 + 2], 0.f);
+    float x[ICP_PPT][3], xt[ICP_PPT][3], nn[ICP_PPT][3];
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, T[3] = {0.f, 0.f, 0.f};
+    if (a.R0)
+        for (int i = 0; i < 9; ++i) R[i] = a.R0[(size_t)b * 9 + i];
+    if (a.T0)
+        for (int i = 0; i < 3; ++i) T[i] = a.T0[(size_t)b * 3 + i];
+    float v[9];
+    v[0] = v[1] = v[2] = 0.f;
+#pragma unroll
+    for (int p = 0; p < ICP_PPT; ++p) {
+        const int i = t + p * ICP_THREADS;
+        const bool ok = i < N;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            x[p][c] = ok ? Xb[i * 3 + c] : 0.f;
+            v[c] += x[p][c];
+        }
+    }
+    icp_block_sum(v, 3, red, bc);
+    const float xmu[3] = {bc[0] / (float)N, bc[1] / (float)N, bc[2] / (float)N};
+    auto apply = [&]() {
+#pragma unroll
+        for (int p = 0; p < ICP_PPT; ++p)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                xt[p][c] = (x[p][0] * R[c] + x[p][1] * R[3 + c] + x[p][2] * R[6 + c]) + T[c];  // bmm(X, R) + T
+    };
+    apply();
+    __syncthreads();
+    float prev = -1.f, rmse = 0.f;
+    int it = 0;
+    bool converged = false;
+    for (; it < a.max_iter; ++it) {
+        // ---- nearest neighbour of every transformed point
+        v[0] = v[1] = v[2] = 0.f;
+#pragma unroll
+        for (int p = 0; p < ICP_PPT; ++p) {
+            const int i = t + p * ICP_THREADS;
+            float best = FLT_MAX;
+            int bj = 0;
+            if (i < N) {
+                for (int j = 0; j < M; ++j) {
+                    const float4 y = sY[j];
+                    const float dx = xt[p][0] - y.x, dy = xt[p][1] - y.y, dz = xt[p][2] - y.z;
+                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d < best) {
+                        best = d;
+                        bj = j;
+                    }
+                }
+                const float4 y = sY[bj];
+                nn[p][0] = y.x;
+                nn[p][1] = y.y;
+                nn[p][2] = y.z;
+            } else {
+                nn[p][0] = nn[p][1] = nn[p][2] = 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] += nn[p][c];
+        }
+        icp_block_sum(v, 3, red, bc);
+        const float ymu[3] = {bc[0] / (float)N, bc[1] / (float)N, bc[2] / (float)N};
+        // ---- XYcov = Xc^T Yc / N
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int p = 0; p < ICP_PPT; ++p) {
+            if (t + p * ICP_THREADS < N) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[r * 3 + c] = fmaf(x[p][r] - xmu[r], nn[p][c] - ymu[c], v[r * 3 + c]);
+            }
+        }
+        icp_block_sum(v, 9, red, bc);
+        if (t == 0) {
+            Mat3 C, U, V;
+            double sig[3];
+            for (int i = 0; i < 9; ++i) C.m[i / 3][i % 3] = (double)(bc[i] / (float)N);
+            svd3(C, U, V, sig);
+            const double dsign = det3(U) * det3(V) < 0 ? -1.0 : 1.0;  // det(U V^T)
+            float Rn[9];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c)
+                    Rn[r * 3 + c] = (float)(U.m[r][0] * V.m[c][0] + U.m[r][1] * V.m[c][1] + dsign * U.m[r][2] * V.m[c][2]);
+            for (int i = 0; i < 9; ++i) bc[i] = Rn[i];
+            for (int c = 0; c < 3; ++c)
+                bc[9 + c] = ymu[c] - (xmu[0] * Rn[c] + xmu[1] * Rn[3 + c] + xmu[2] * Rn[6 + c]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = bc[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) T[c] = bc[9 + c];
+        __syncthreads();
+        apply();
+        // ---- rmse and the relative-improvement test
+        v[0] = 0.f;
+#pragma unroll
+        for (int p = 0; p < ICP_PPT; ++p) {
+            if (t + p * ICP_THREADS < N) {
+                const float dx = xt[p][0] - nn[p][0], dy = xt[p][1] - nn[p][1], dz = xt[p][2] - nn[p][2];
+                v[0] += dx * dx + dy * dy + dz * dz;
+            }
+        }
+        icp_block_sum(v, 1, red, bc);
+        rmse = sqrtf(bc[0] / (float)N);
+        if (t == 0) s_stop = (prev >= 0.f && (prev - rmse) / prev <= a.rel_thr) ? 1 : 0;
+        __syncthreads();
+        if (s_stop) {
+            converged = true;
+            ++it;
+            break;
+        }
+        prev = rmse;
+    }
+    if (t < 9) a.R[(size_t)b * 9 + t] = R[t];
+    if (t < 3) a.T[(size_t)b * 3 + t] = T[t];
+    if (t == 0) {
+        a.rmse[b] = rmse;
+        a.n_iter[b] = converged ? it : -it;
+    }
+    if (a.Xt) {
+#pragma unroll
+        for (int p = 0; p < ICP_PPT; ++p) {
+            const int i = t + p * ICP_THREADS;
+            if (i < N)
+                for (int c = 0; c < 3; ++c) a.Xt[((size_t)b * N + i) * 3 + c] = xt[p][c];
+        }
+    }
+}
+
 int fill_table(const int32_t* off0, const int32_t* off1, int first, int count, int dim, size_t ws_base,
                PairTable& tab, size_t& ws_end, int& max_nm, int& max_n_plus_m) {
     tab.n_pairs = count;
@@ -537,6 +714,33 @@ int ls_kabsch_from_codes(const float* z_so3_a, const float* t_a, const float* z_
     a.res = res;
     k_kabsch<true><<<(n_pairs + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
     LS_CHECK_LAUNCH("k_kabsch_codes");
+    return LS_OK;
+}
+
+int ls_icp(const float* X, const float* Y, int32_t B, int32_t N, int32_t M, const float* R0, const float* T0,
+           int32_t max_iterations, float relative_rmse_thr, float* R, float* T, float* rmse, int32_t* n_iter, float* Xt,
+           void* stream) {
+    LS_REQUIRE(X && Y && R && T && rmse && n_iter, "null pointer");
+    LS_REQUIRE(B >= 1 && N >= 1 && N <= ICP_THREADS * ICP_PPT && M >= 1 && M <= 12288, "icp: need N <= 4096, M <= 12288");
+    LS_REQUIRE(max_iterations >= 1, "icp: max_iterations must be >= 1");
+    IcpArgs a{};
+    a.X = X;
+    a.Y = Y;
+    a.R0 = R0;
+    a.T0 = T0;
+    a.N = N;
+    a.M = M;
+    a.max_iter = max_iterations;
+    a.rel_thr = relative_rmse_thr;
+    a.R = R;
+    a.T = T;
+    a.rmse = rmse;
+    a.n_iter = n_iter;
+    a.Xt = Xt;
+    const size_t smem = (size_t)M * sizeof(float4);
+    LS_CHECK_CUDA(cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_icp<<<B, ICP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    LS_CHECK_LAUNCH("k_icp");
     return LS_OK;
 }
 

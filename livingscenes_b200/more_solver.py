@@ -1,17 +1,17 @@
 """More_Solver -- the inference orchestration of lib_more/more_solver.py on the CUDA hot path.
 
 Built: ``_solve_object_matching`` (more_solver.py:71-93, methods "sequential" and "nn"),
-``_solve_pairwise_registration(pc1, pc2, optim=False)`` (:95-116: FPS to n_input_point, encode both,
-Kabsch on z_so3 + t) and a batched ``solve_scene_pair`` that does encode -> match -> pose for two
+``_solve_pairwise_registration(pc1, pc2, optim=False)`` (:95-116,182-189: FPS to n_input_point, encode both,
+Kabsch on z_so3 + t, ICP refinement) and a batched ``solve_scene_pair`` that does encode -> match -> pose for two
 instance sets without leaving the GPU.  Out of scope: the ``optim=True`` SE(3) Adam
-loop, ``_optimize_code``, ICP refinement and mesh extraction.
+loop, ``_optimize_code`` and mesh extraction.
 """
 from __future__ import annotations
 
 import torch
 
 from .matcher_new import nn_matcher, sequential_matcher
-from .ops import farthest_point_sample
+from .ops import SimilarityTransform, farthest_point_sample, iterative_closest_point
 from .pose_estimation import kabsch_from_codes, kabsch_transformation_estimation
 
 
@@ -35,17 +35,25 @@ class More_Solver:
                                   "(sinkhorn / sim3_seq / eq_seq: SURVEY.md 8f rank 4)")
 
     @torch.no_grad()
-    def _solve_pairwise_registration(self, pc1_full, pc2_full, optim=False):
-        """pc1 [1,N,3], pc2 [1,M,3] -> R [1,3,3], t [1,3,1] (direction pc1 -> pc2)."""
+    def _solve_pairwise_registration(self, pc1_full, pc2_full, optim=False, icp=True):
+        """pc1 [1,N,3], pc2 [1,M,3] -> R [1,3,3], t [1,3,1] (direction pc1 -> pc2).  ``icp=False`` returns the
+        code-based Kabsch pose without the ICP refinement the reference always applies."""
         if optim:
-            raise NotImplementedError("optim=True (SE(3) Adam refinement + ICP) is out of scope (SURVEY.md 8f)")
+            raise NotImplementedError("optim=True (SE(3) Adam refinement) is out of scope (SURVEY.md 8f)")
         n_in = self.cfg["shape_priors"]["n_input_point"]
         _, pc1 = farthest_point_sample(pc1_full.transpose(1, 2), n_in)
         _, pc2 = farthest_point_sample(pc2_full.transpose(1, 2), n_in)
         code1 = self.model.encode(pc1)
         code2 = self.model.encode(pc2)
         R, t, _, _ = kabsch_transformation_estimation(code1["z_so3"] + code1["t"], code2["z_so3"] + code2["t"])
-        return R, t
+        if not icp:
+            return R, t
+        # ICP refinement on the sub-sampled clouds, initialised with the code-based pose (more_solver.py:182-189)
+        s0 = torch.ones(R.shape[0], device=R.device)
+        sol = iterative_closest_point(pc1.transpose(1, 2), pc2.transpose(1, 2),
+                                      init_transform=SimilarityTransform(R.transpose(-1, -2), t.squeeze(2), s0))
+        R, t, _ = sol.RTs
+        return R.transpose(-1, -2), t.unsqueeze(2)
 
     @torch.no_grad()
     def solve_scene_pair(self, ref_pcs, rescan_pcs, method="sequential"):

@@ -3,9 +3,11 @@
   knn_points              pytorch3d.ops.knn.knn_points as called at vec_dgcnn_atten.py:139-141
   sample_farthest_points  pytorch3d.ops.sample_farthest_points (vec_dgcnn_atten.py:169,
                           model_utils.py:205, more_solver.py:67,107-108)
+  iterative_closest_point pytorch3d.ops.iterative_closest_point (more_solver.py:182-187)
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 
 import torch
@@ -112,6 +114,49 @@ def sample_farthest_points(points: torch.Tensor, K: int = 50, random_start_point
         start = torch.randint(0, points.shape[1], (points.shape[0],), dtype=torch.int64)
     idx, out = farthest_point_sample(points.transpose(1, 2), K, start)
     return out.transpose(1, 2).to(points.dtype), idx
+
+
+SimilarityTransform = collections.namedtuple("SimilarityTransform", ["R", "T", "s"])
+ICPSolution = collections.namedtuple("ICPSolution", ["converged", "rmse", "Xt", "RTs", "t_history"])
+
+
+@torch.no_grad()
+def iterative_closest_point(X: torch.Tensor, Y: torch.Tensor, init_transform=None, max_iterations: int = 100,
+                            relative_rmse_thr: float = 1e-6, estimate_scale: bool = False,
+                            allow_reflection: bool = False):
+    """pytorch3d.ops.iterative_closest_point as called at more_solver.py:183 (tensors, equal lengths, rigid):
+    X [B,N,3], Y [B,M,3], ``init_transform`` = (R [B,3,3], T [B,3], s [B]) in pytorch3d's row-vector convention
+    (Xt = s X R + T).  Returns ICPSolution(converged, rmse [B], Xt [B,N,3], SimilarityTransform(R, T, s), []);
+    ``t_history`` is not recorded.  One CTA per pair runs the whole loop (ls_icp)."""
+    if estimate_scale or allow_reflection:
+        raise NotImplementedError("ls_icp is built for the reference's call: estimate_scale=False, allow_reflection=False")
+    _lib.require_cuda(X, "X")
+    B, N, _ = X.shape
+    M = Y.shape[1]
+    x = X.detach().float().contiguous()
+    y = Y.detach().float().contiguous()
+    R0 = T0 = None
+    if init_transform is not None:
+        R0, T0, s0 = init_transform
+        if not torch.all(s0 == 1):
+            raise NotImplementedError("ls_icp: the initial scale must be 1 (rigid ICP)")
+        R0 = R0.detach().float().expand(B, 3, 3).contiguous()
+        T0 = T0.detach().float().expand(B, 3).contiguous()
+    dev = x.device
+    R = torch.empty(B, 3, 3, device=dev)
+    T = torch.empty(B, 3, device=dev)
+    rmse = torch.empty(B, device=dev)
+    n_it = torch.empty(B, dtype=torch.int32, device=dev)
+    Xt = torch.empty(B, N, 3, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ls_icp(x.data_ptr(), y.data_ptr(), B, N, M, _lib.ptr(R0), _lib.ptr(T0), int(max_iterations),
+                               float(relative_rmse_thr), R.data_ptr(), T.data_ptr(), rmse.data_ptr(), n_it.data_ptr(),
+                               Xt.data_ptr(), _lib.stream_ptr(dev))
+        _lib.check(rc, "ls_icp")
+        _lib.launch_count += 1
+    sol = ICPSolution(bool((n_it > 0).all()), rmse, Xt, SimilarityTransform(R, T, torch.ones(B, device=dev)), [])
+    sol.RTs.R.n_iter = n_it  # iterations per pair (negative: not converged), for diagnostics
+    return sol
 
 
 @torch.no_grad()

@@ -36,6 +36,7 @@ fp32 summation order is not observable here):
 """
 from __future__ import annotations
 
+import collections
 import sys
 import types
 
@@ -120,6 +121,60 @@ def sample_farthest_points(points, lengths=None, K: int = 50, random_start_point
     return pts.to(points.device), idx.to(points.device)
 
 
+SimilarityTransform = collections.namedtuple("SimilarityTransform", ["R", "T", "s"])
+ICPSolution = collections.namedtuple("ICPSolution", ["converged", "rmse", "Xt", "RTs", "t_history"])
+
+
+def corresponding_points_alignment(X, Y, weights=None, estimate_scale=False, allow_reflection=False, eps=1e-9):
+    """pytorch3d 0.7.4 ops/points_alignment.py corresponding_points_alignment (restated from memory; pytorch3d is
+    not vendored and the reference has no test vectors for it: parity unpinned).  Row-vector convention."""
+    assert weights is None and not estimate_scale and not allow_reflection
+    b, n, dim = X.shape
+    Xmu, Ymu = X.mean(1, keepdim=True), Y.mean(1, keepdim=True)
+    Xc, Yc = X - Xmu, Y - Ymu
+    XYcov = torch.bmm(Xc.transpose(2, 1), Yc) / float(n)
+    U, S, Vh = torch.linalg.svd(XYcov)
+    V = Vh.transpose(2, 1)
+    E = torch.eye(dim, dtype=XYcov.dtype)[None].repeat(b, 1, 1)
+    E[:, -1, -1] = torch.det(torch.bmm(U, V.transpose(2, 1)))
+    R = torch.bmm(torch.bmm(U, E), V.transpose(2, 1))
+    s = torch.ones(b, dtype=X.dtype)
+    T = Ymu[:, 0, :] - s[:, None] * torch.bmm(Xmu, R)[:, 0, :]
+    return SimilarityTransform(R, T, s)
+
+
+def iterative_closest_point(X, Y, init_transform=None, max_iterations=100, relative_rmse_thr=1e-6,
+                            estimate_scale=False, allow_reflection=False, verbose=False):
+    """pytorch3d 0.7.4 ops/points_alignment.py iterative_closest_point for equal-length tensors (restated from
+    memory, see above): Xt = s X R + T; loop {1-NN of Xt in Y, alignment of X_init with the NN points, rmse,
+    stop when (prev - rmse) / prev <= thr}."""
+    assert not estimate_scale and not allow_reflection
+    Xt, Yt = X.detach().cpu().float(), Y.detach().cpu().float()
+    b = Xt.shape[0]
+    Xt_init = Xt.clone()
+    if init_transform is not None:
+        R, T, s = (t.detach().cpu().float() for t in init_transform)
+        Xt = s[:, None, None] * torch.bmm(Xt, R) + T[:, None, :]
+    else:
+        R, T, s = torch.eye(3)[None].repeat(b, 1, 1), torch.zeros(b, 3), torch.ones(b)
+    prev_rmse, rmse, converged, n_iter = None, None, False, 0
+    for _ in range(max_iterations):
+        n_iter += 1
+        d = ((Xt[:, :, None, :] - Yt[:, None, :, :]) ** 2).sum(-1)  # [b,N,M]
+        nn_idx = d.argmin(-1)
+        Xt_nn = torch.gather(Yt, 1, nn_idx[..., None].expand(-1, -1, 3))
+        R, T, s = corresponding_points_alignment(Xt_init, Xt_nn)
+        Xt = s[:, None, None] * torch.bmm(Xt_init, R) + T[:, None, :]
+        rmse = ((Xt - Xt_nn) ** 2).sum(2).mean(1).sqrt()
+        relative = torch.ones(b) if prev_rmse is None else (prev_rmse - rmse) / prev_rmse
+        if bool((relative <= relative_rmse_thr).all()):
+            converged = True
+            break
+        prev_rmse = rmse
+    sol = ICPSolution(converged, rmse, Xt, SimilarityTransform(R, T, s), [])
+    return sol
+
+
 def install() -> None:
     """Register the shim as ``pytorch3d.ops`` / ``pytorch3d.ops.knn`` in sys.modules."""
     if "pytorch3d" in sys.modules and getattr(sys.modules["pytorch3d"], "__oracle_shim__", False):
@@ -136,11 +191,10 @@ def install() -> None:
     ops.sample_farthest_points = sample_farthest_points
     ops.knn = knn
 
-    def _icp(*a, **k):
-        raise NotImplementedError("ICP is out of scope (SURVEY.md section 8f)")
-
-    ops.iterative_closest_point = _icp
-    pa.SimilarityTransform = object
+    ops.iterative_closest_point = iterative_closest_point
+    ops.corresponding_points_alignment = corresponding_points_alignment
+    pa.iterative_closest_point = iterative_closest_point
+    pa.SimilarityTransform = SimilarityTransform
     ops.points_alignment = pa
     root.ops = ops
     sys.modules["pytorch3d"] = root

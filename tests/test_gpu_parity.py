@@ -631,3 +631,64 @@ def test_sdf_chunking_is_consistent(dev, oracle_R):
     with torch.no_grad():
         ref = oracle_R.sdf_decode(state_dict_for("random"), q[:, :4096].cpu(), {k: v.cpu() for k, v in code.items()})
     assert float((both[:, :4096].cpu() - ref).abs().max()) < TOL
+
+
+# ------------------------------------------------------------------------------------------ ICP refinement
+@pytest.mark.parametrize("N,M,with_init", [(1024, 1024, True), (700, 1500, False), (1024, 1024, False)])
+def test_icp_matches_oracle(N, M, with_init, dev):
+    """ls_icp against the restated pytorch3d iterative_closest_point (more_solver.py:182-187)."""
+    import math
+
+    from livingscenes_b200.ops import SimilarityTransform, iterative_closest_point
+    from oracle import p3d_shim
+
+    g = torch.Generator().manual_seed(N + M)
+    B = 3
+    Y = torch.randn(B, M, 3, generator=g) * torch.tensor([1.0, 0.6, 0.8])
+    ang = torch.tensor([0.12, -0.2, 0.05])
+    Rz = torch.stack([torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+                      for a in ang.tolist()])
+    X = torch.bmm(Y[:, :N] if N <= M else Y.repeat(1, 2, 1)[:, :N], Rz) + torch.tensor([0.05, -0.03, 0.02])
+    X = X + 0.002 * torch.randn(B, N, 3, generator=g)
+    init = None
+    if with_init:
+        init = SimilarityTransform(Rz.transpose(1, 2) @ torch.eye(3), torch.tensor([[-0.04, 0.02, -0.01]]).repeat(B, 1),
+                                   torch.ones(B))
+    ref = p3d_shim.iterative_closest_point(X, Y, init_transform=init)
+    dinit = None if init is None else SimilarityTransform(*(t.to(dev) for t in init))
+    sol = iterative_closest_point(X.to(dev), Y.to(dev), init_transform=dinit)
+    torch.cuda.synchronize()
+    assert sol.converged == ref.converged
+    assert float((sol.RTs.R.cpu() - ref.RTs.R).abs().max()) < TOL
+    assert float((sol.RTs.T.cpu() - ref.RTs.T).abs().max()) < TOL
+    assert float((sol.Xt.cpu() - ref.Xt).abs().max()) < 5 * TOL
+    assert float((sol.rmse.cpu() - ref.rmse).abs().max()) < TOL
+    assert float((torch.det(sol.RTs.R.cpu()) - 1).abs().max()) < 1e-5
+
+
+def test_pairwise_registration_with_icp(dev, oracle_R):
+    """More_Solver._solve_pairwise_registration (more_solver.py:95-116,182-189): FPS -> encode -> Kabsch on the
+    equivariant codes -> ICP, against the oracle chain on the same clouds."""
+    import livingscenes_b200 as ls
+    from oracle import p3d_shim
+
+    sd = state_dict_for("random")
+    model = _model("random", dev)
+    solver = ls.More_Solver(model)
+    pc1 = oracle_R.synth_instances(1, 1500, 31).transpose(1, 2).contiguous()  # [1,N,3]
+    Rg = oracle_R.random_rotations(1, 32)[0]
+    pc2 = (pc1 @ Rg.T) + torch.tensor([0.2, -0.1, 0.3])
+    R, t = solver._solve_pairwise_registration(pc1.to(dev), pc2.to(dev))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        s1, _ = p3d_shim.sample_farthest_points(pc1, K=1024)
+        s2, _ = p3d_shim.sample_farthest_points(pc2, K=1024)
+        c1, c2 = oracle_R.encode(sd, s1.transpose(1, 2).contiguous()), oracle_R.encode(sd, s2.transpose(1, 2).contiguous())
+        Rk, tk, _ = oracle_R.kabsch(c1["z_so3"] + c1["t"], c2["z_so3"] + c2["t"])
+        ref = p3d_shim.iterative_closest_point(
+            s1, s2, init_transform=p3d_shim.SimilarityTransform(Rk.transpose(-1, -2), tk.squeeze(2), torch.ones(1)))
+    Rr, tr = ref.RTs.R.transpose(-1, -2), ref.RTs.T.unsqueeze(2)
+    assert float((R.cpu() - Rr).abs().max()) < 5 * TOL and float((t.cpu() - tr).abs().max()) < 5 * TOL
+    # the refined pose maps pc1 onto pc2
+    err = ((pc1 @ R.cpu()[0].T + t.cpu()[0].T) - pc2).norm(dim=-1).max()
+    assert float(err) < 1e-3
