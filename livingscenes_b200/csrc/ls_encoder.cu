@@ -93,7 +93,15 @@ struct Carver {
     }
 };
 
-constexpr int SMALL_NS = 128;  // source sets up to this size take the k_knn_small path
+constexpr int SMALL_NS = 128;  // source sets up to this size take the k_knn_small path (brute-force graph only)
+// with the tensor-core graph enabled, source sets down to this size still go through k_knn_tc
+int small_tc_min() {
+    static const int v = [] {
+        const char* e = getenv("LS_SMALL_TC_MIN");
+        return e ? atoi(e) : 129;
+    }();
+    return v;
+}
 bool g_use_knn_tc = true;      // tensor-core candidate filter for the larger source sets
 float g_knn_tc_kappa_scale = 1.f;
 
@@ -150,9 +158,8 @@ void make_plan(const ls_encoder_desc* d, int B, int N, void* ws, Plan& p) {
         n /= L.down_factor;
         p.n_dst[i] = n;
         const size_t co = L.c_out, ci = L.c_in;
-        if (p.n_src[i] <= SMALL_NS) {
-            small = std::max(small, (size_t)n * LS_KNN_K);
-        } else {
+        if (p.n_src[i] <= SMALL_NS) small = std::max(small, (size_t)n * LS_KNN_K);
+        {
             const int D = (int)ci * 3;
             kimg_s = std::max(kimg_s, knn_tc_img_floats(p.n_src[i], D));
             knrm_s = std::max(knrm_s, knn_tc_nrm_floats(p.n_src[i]));
@@ -491,7 +498,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         }
 
         // ---- kNN graph
-        if (ea.idx_in == nullptr && Ns <= SMALL_NS) {
+        if (ea.idx_in == nullptr && Ns <= SMALL_NS && !(g_use_knn_tc && Ns >= small_tc_min())) {
             ProfScope ps(4, i, st);
             dim3 gs((Nd + 7) / 8, B);
             k_knn_small<<<gs, 256, 0, st>>>(src_f, dst_f, Ci * 3, Ns, Nd, p.small_idx, nullptr);
