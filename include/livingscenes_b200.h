@@ -190,6 +190,14 @@ LS_API int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t
 LS_API int ls_fps_workspace_bytes(int32_t B, int32_t N, size_t* bytes);
 LS_API int ls_fps_ex(const float* xyz, int32_t B, int32_t N, int32_t n_out, const int64_t* start_idx, int64_t* idx,
               float* out_xyz, void* workspace, size_t workspace_bytes, void* stream);
+/* FPS of a whole batch of ragged, masked instances in ONE launch (Shape_Prior.encode_fps, model_utils.py:199-205:
+ * valid_pc = pc.T[mask]; fps(valid_pc, K)): xyz [B,3,Nmax], mask [B,Nmax] bytes (non-zero = valid).  The valid
+ * points of every instance are compacted in order into the workspace (B*Nmax float4) and sampled there; idx
+ * (optional [B,n_out]) refers to the compacted list like pytorch3d's; out_xyz (optional) [B,3,n_out]; n_valid
+ * (optional [B]) receives the number of valid points -- callers must check n_valid >= n_out.  start_idx as ls_fps_ex. */
+LS_API int ls_fps_masked(const float* xyz, const uint8_t* mask, int32_t B, int32_t Nmax, int32_t n_out,
+                  const int64_t* start_idx, int64_t* idx, float* out_xyz, int32_t* n_valid, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Matching: lib_more/matcher_new.py

@@ -89,6 +89,8 @@ _PROTOS = {
     "ls_fps_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "ls_fps_ex": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_size_t, C.c_void_p]),
+    "ls_fps_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ls_match_workspace_bytes": (C.c_int, [c_i32_p, c_i32_p, C.c_int32, C.POINTER(C.c_size_t)]),
     "ls_seq_match": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, c_i32_p, c_i32_p, C.c_int32, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -828,6 +828,19 @@ int ls_fps_ex(const float* xyz, int32_t B, int32_t N, int32_t n_out, const int64
     return launch_fps(fa, B, st);
 }
 
+int ls_fps_masked(const float* xyz, const uint8_t* mask, int32_t B, int32_t Nmax, int32_t n_out, const int64_t* start_idx,
+                  int64_t* idx, float* out_xyz, int32_t* n_valid, void* workspace, size_t workspace_bytes, void* stream) {
+    LS_REQUIRE(xyz && mask && (idx || out_xyz), "null pointer");
+    LS_REQUIRE(B >= 1 && Nmax >= 1 && n_out >= 1, "fps_masked: bad sizes");
+    LS_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)B * Nmax * sizeof(float4),
+               "fps_masked: workspace must hold B * Nmax float4");
+    LS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "fps_masked: workspace must be 16-byte aligned");
+    k_fps_masked<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(xyz, mask, Nmax, n_out, start_idx,
+                                                                     static_cast<float4*>(workspace), n_valid, idx, out_xyz);
+    LS_CHECK_LAUNCH("k_fps_masked");
+    return LS_OK;
+}
+
 int ls_fps(const float* xyz, int32_t B, int32_t N, int32_t n_out, int64_t* idx, float* out_xyz, void* stream) {
     LS_REQUIRE(N <= 8192, "ls_fps: N > 8192 needs ls_fps_ex with a workspace");
     return ls_fps_ex(xyz, B, N, n_out, nullptr, idx, out_xyz, nullptr, 0, stream);

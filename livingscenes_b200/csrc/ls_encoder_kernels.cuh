@@ -255,31 +255,30 @@ __global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
     }
 }
 
-// Large clouds (N > 8192: scene-level instances of up to ~10^5 points, model_utils.py:199-205): one CTA per
-// instance, the running min-distance lives in a caller-provided scratch as float4 {x,y,z,min_d} per point (L2
-// resident: one 16-byte load and one 4-byte store per point and step), same arithmetic and tie rule as k_fps.
-__global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xyz, int N, int n_out,
-                                                    const int64_t* __restrict__ start, float4* __restrict__ scr,
-                                                    int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+// Large / ragged clouds (N > 8192, or masked instances of different sizes: model_utils.py:199-205): one CTA per
+// instance, the points and the running min-distance live in a caller-provided scratch as float4 {x,y,z,min_d}
+// per point (L2 resident: one 16-byte load and one 4-byte store per point and step), same arithmetic and tie rule
+// as k_fps.  With a mask the valid points are first compacted (stable order, like pc.T[mask]) into the scratch, so
+// a whole batch of ragged instances is sampled by ONE launch; indices then refer to the compacted list.
+__device__ __forceinline__ void fps_scratch_loop(float4* __restrict__ sb, int N, int n_out, int last, int b,
+                                                 int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
     __shared__ float wb_v[2][32];
     __shared__ int wb_i[2][32];
-    const int T = blockDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
-    const float* xb = xyz + (size_t)b * 3 * N;
-    float4* sb = scr + (size_t)b * N;
-    for (int i = t; i < N; i += T) sb[i] = make_float4(xb[i], xb[N + i], xb[2 * N + i], FLT_MAX);
-    int last = start ? (int)start[b] : 0;
-    if (t == 0) {
-        sel64[(size_t)b * n_out] = last;
+    const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
+    auto publish = [&](int j, int sel) {
+        if (sel64) sel64[(size_t)b * n_out + j] = sel;
         if (out_xyz) {
-            float* o = out_xyz + (size_t)b * 3 * n_out;
-            o[0] = xb[last];
-            o[n_out] = xb[N + last];
-            o[2 * n_out] = xb[2 * N + last];
+            const float4 p = sb[sel];
+            float* o = out_xyz + (size_t)b * 3 * n_out + j;
+            o[0] = p.x;
+            o[n_out] = p.y;
+            o[2 * n_out] = p.z;
         }
-    }
-    __syncthreads();
+    };
+    if (t == 0) publish(0, last);
     for (int j = 1; j < n_out; ++j) {
-        const float lx = __ldg(xb + last), ly = __ldg(xb + N + last), lz = __ldg(xb + 2 * N + last);
+        const float4 lp = sb[last];
+        const float lx = lp.x, ly = lp.y, lz = lp.z;
         float bv = -2.f;
         int bi = 0x7fffffff;
         for (int i = t; i < N; i += T) {
@@ -320,16 +319,58 @@ __global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xy
             }
         }
         last = bi;
-        if (t == 0) {
-            sel64[(size_t)b * n_out + j] = last;
-            if (out_xyz) {
-                float* o = out_xyz + (size_t)b * 3 * n_out + j;
-                o[0] = xb[last];
-                o[n_out] = xb[N + last];
-                o[2 * n_out] = xb[2 * N + last];
-            }
-        }
+        if (t == 0) publish(j, last);
     }
+}
+
+__global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xyz, int N, int n_out,
+                                                    const int64_t* __restrict__ start, float4* __restrict__ scr,
+                                                    int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+    const int T = blockDim.x, b = blockIdx.x, t = threadIdx.x;
+    const float* xb = xyz + (size_t)b * 3 * N;
+    float4* sb = scr + (size_t)b * N;
+    for (int i = t; i < N; i += T) sb[i] = make_float4(xb[i], xb[N + i], xb[2 * N + i], FLT_MAX);
+    __syncthreads();
+    fps_scratch_loop(sb, N, n_out, start ? (int)start[b] : 0, b, sel64, out_xyz);
+}
+
+// xyz [B][3][Nmax], mask [B][Nmax] (bytes, non-zero = valid).  n_valid[b] receives the number of valid points; an
+// instance with fewer valid points than n_out repeats point 0 once its points are exhausted (callers check n_valid).
+__global__ void __launch_bounds__(1024) k_fps_masked(const float* __restrict__ xyz, const unsigned char* __restrict__ mask,
+                                                     int Nmax, int n_out, const int64_t* __restrict__ start,
+                                                     float4* __restrict__ scr, int32_t* __restrict__ n_valid,
+                                                     int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int T = blockDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
+    const float* xb = xyz + (size_t)b * 3 * Nmax;
+    const unsigned char* mb = mask + (size_t)b * Nmax;
+    float4* sb = scr + (size_t)b * Nmax;
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (int c = 0; c < Nmax; c += T) {  // stable compaction, one block-wide prefix sum per chunk of T points
+        const int i = c + t;
+        const bool ok = i < Nmax && mb[i] != 0;
+        const unsigned bal = __ballot_sync(FULL, ok);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < w; ++k) off += s_warp[k];
+        if (ok) sb[off + __popc(bal & ((1u << lane) - 1u))] = make_float4(xb[i], xb[Nmax + i], xb[2 * Nmax + i], FLT_MAX);
+        __syncthreads();
+        if (t == 0) {
+            int tot = 0;
+            for (int k = 0; k < nw; ++k) tot += s_warp[k];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    const int N = s_base;
+    if (t == 0 && n_valid) n_valid[b] = N;
+    if (N == 0) return;
+    int first = start ? (int)start[b] : 0;
+    first = min(max(first, 0), N - 1);
+    fps_scratch_loop(sb, N, n_out, first, b, sel64, out_xyz);
 }
 
 // dst_f[b][r][j] = src_f[b][r][sel[b][j]]   (vec_dgcnn_atten.py:173; r runs over C*3 rows)

@@ -130,27 +130,32 @@ class Shape_Prior(nn.Module):
     def encode_fps(self, batch_pc, batch_mask, n_fps=1):
         """batch_pc [B,3,Nmax], batch_mask [B,1,Nmax] bool (model_utils.py:199-215): per instance keep the
         valid points, FPS to ``field_input_n`` (start index 0; ``n_fps`` > 1: that many random start indices per
-        instance, codes averaged), encode.  The FPS runs per instance (ragged sizes, up to ~10^5 points) but the
-        encoder runs ONCE on the whole batch instead of B times with B = n_fps."""
+        instance, codes averaged), encode.  The whole ragged batch is sampled by ONE launch (``ls_fps_masked``
+        compacts the valid points of every instance and runs FPS on them, up to ~10^5 points each) and encoded by
+        ONE batched encoder call instead of B python iterations with B = n_fps."""
         assert batch_pc.shape[-1] == batch_mask.shape[-1], "point cloud and mask must have same length!"
-        from .ops import farthest_point_sample
+        from .ops import farthest_point_sample_masked
 
         n_fps = int(n_fps)
         assert n_fps >= 1
-        pcs = []
-        for pc, mask in zip(batch_pc, batch_mask):
-            valid = pc[:, mask.reshape(-1)].unsqueeze(0).contiguous()  # [1,3,Nv]
-            if n_fps == 1:
-                _, sub = farthest_point_sample(valid, self.field_input_n)
-            else:  # random restarts (model_utils.py:202,205): first index drawn per restart, codes averaged below
-                start = torch.randint(0, valid.shape[-1], (n_fps,), dtype=torch.int64)
-                _, sub = farthest_point_sample(valid.expand(n_fps, -1, -1).contiguous(), self.field_input_n, start)
-            pcs.append(sub)
-        code = self.encode(torch.cat(pcs, 0))
+        B = batch_pc.shape[0]
+        mask = batch_mask.reshape(B, -1)
+        n_valid = mask.sum(-1)
+        if int(n_valid.min()) < self.field_input_n:
+            raise ValueError(f"encode_fps: an instance has {int(n_valid.min())} valid points, fewer than the "
+                             f"{self.field_input_n} the encoder samples")
+        if n_fps == 1:
+            pc, mk, start = batch_pc, mask, None
+        else:  # random restarts (model_utils.py:202,205): first index drawn per restart, codes averaged below
+            pc = batch_pc.repeat_interleave(n_fps, dim=0)
+            mk = mask.repeat_interleave(n_fps, dim=0)
+            nv = n_valid.repeat_interleave(n_fps).cpu().double()
+            start = torch.minimum((torch.rand(B * n_fps, dtype=torch.float64) * nv).long(), nv.long() - 1)
+        sub, _ = farthest_point_sample_masked(pc, mk, self.field_input_n, start)  # ONE launch for the ragged batch
+        code = self.encode(sub)
         if n_fps == 1:
             return code
         # average the embeddings of the restarts of each instance (model_utils.py:209)
-        B = len(pcs)
         return {k: v.reshape(B, n_fps, *v.shape[1:]).mean(1) for k, v in code.items()}
 
     def forward(self, x):

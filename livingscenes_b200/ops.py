@@ -105,6 +105,30 @@ def farthest_point_sample(xyz_cm: torch.Tensor, n_out: int, start_idx: torch.Ten
     return idx, out
 
 
+@torch.no_grad()
+def farthest_point_sample_masked(xyz_cm: torch.Tensor, mask: torch.Tensor, n_out: int, start_idx: torch.Tensor = None):
+    """Batched FPS of ragged instances: xyz [B,3,Nmax], mask [B,Nmax] (or [B,1,Nmax]) bool -> (sampled xyz
+    [B,3,n_out], n_valid [B] int32).  One launch for the whole batch; equivalent to FPS of ``pc[:, mask]`` per
+    instance (model_utils.py:203-205)."""
+    _lib.require_cuda(xyz_cm, "xyz")
+    B, three, Nmax = xyz_cm.shape
+    assert three == 3
+    x = xyz_cm.detach().float().contiguous()
+    m = mask.reshape(B, Nmax).to(device=x.device, dtype=torch.uint8).contiguous()
+    out = torch.empty(B, 3, n_out, dtype=torch.float32, device=x.device)
+    nv = torch.empty(B, dtype=torch.int32, device=x.device)
+    ws = torch.empty(B * Nmax * 16, dtype=torch.uint8, device=x.device)
+    st = None
+    if start_idx is not None:
+        st = start_idx.to(device=x.device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().ls_fps_masked(x.data_ptr(), m.data_ptr(), B, Nmax, n_out, _lib.ptr(st), None, out.data_ptr(),
+                                      nv.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device))
+        _lib.check(rc, "ls_fps_masked")
+        _lib.launch_count += 1
+    return out, nv
+
+
 def sample_farthest_points(points: torch.Tensor, K: int = 50, random_start_point: bool = False):
     """pytorch3d signature: points [B,P,3] -> (pts [B,K,3], idx [B,K]).  ``random_start_point`` draws the first
     index per instance from torch's global RNG (pytorch3d draws it from its own RNG: the sequences differ, the

@@ -301,11 +301,12 @@ def test_encode_fps_random_restarts(dev, oracle_R):
     torch.cuda.synchronize()
     torch.manual_seed(123)
     ref = {k: [] for k in ("z_so3", "z_inv", "s", "t")}
+    nv = mask.reshape(B, -1).sum(-1).repeat_interleave(n_fps).double()
+    starts = torch.minimum((torch.rand(B * n_fps, dtype=torch.float64) * nv).long(), nv.long() - 1).reshape(B, n_fps)
     with torch.no_grad():
         for b in range(B):
             valid = pc[b][:, mask[b, 0]]
-            start = torch.randint(0, valid.shape[-1], (n_fps,), dtype=torch.int64)
-            sub, _ = ref_fps(valid.T[None].expand(n_fps, -1, -1).contiguous(), K=model.field_input_n, start_idx=start)
+            sub, _ = ref_fps(valid.T[None].expand(n_fps, -1, -1).contiguous(), K=model.field_input_n, start_idx=starts[b])
             code = oracle_R.encode(sd, sub.transpose(1, 2).contiguous())
             for k in ref:
                 ref[k].append(code[k].mean(0, keepdim=True))
@@ -313,6 +314,16 @@ def test_encode_fps_random_restarts(dev, oracle_R):
         r = torch.cat(ref[k], 0)
         assert out[k].shape == r.shape, k
         assert relerr(out[k].cpu(), r) < TOL, k
+    # deterministic path of the evals (n_fps = 1, start index 0)
+    out1 = model.encode_fps(pc.to(dev), mask.to(dev))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        subs = [ref_fps(pc[b][:, mask[b, 0]].T[None].contiguous(), K=model.field_input_n)[0] for b in range(B)]
+        code1 = oracle_R.encode(sd, torch.cat(subs, 0).transpose(1, 2).contiguous())
+    for k in ("z_so3", "z_inv", "s", "t"):
+        assert relerr(out1[k].cpu(), code1[k]) < TOL, k
+    with pytest.raises(ValueError):
+        model.encode_fps(pc[:, :, :900].to(dev), torch.ones(B, 1, 900, dtype=torch.bool, device=dev))
 
 
 @pytest.mark.parametrize("N,n_out", [(1024, 512), (2048, 1024), (1000, 77), (5000, 1024), (16, 16)])
@@ -692,3 +703,26 @@ def test_pairwise_registration_with_icp(dev, oracle_R):
     # the refined pose maps pc1 onto pc2
     err = ((pc1 @ R.cpu()[0].T + t.cpu()[0].T) - pc2).norm(dim=-1).max()
     assert float(err) < 1e-3
+
+
+def test_fps_masked_batch_equals_per_instance(dev):
+    """ls_fps_masked: one launch over a ragged masked batch == FPS of pc[:, mask] per instance (oracle), incl. a
+    large instance and scattered masks."""
+    from livingscenes_b200.ops import farthest_point_sample_masked
+    from oracle.p3d_shim import sample_farthest_points as ref_fps
+
+    g = torch.Generator().manual_seed(21)
+    B, Nmax, n_out = 3, 12000, 1024
+    pc = torch.randn(B, 3, Nmax, generator=g)
+    mask = torch.zeros(B, Nmax, dtype=torch.bool)
+    mask[0, :11000] = True
+    mask[1] = torch.rand(Nmax, generator=g) < 0.3
+    mask[2, 5000:6500] = True
+    start = torch.tensor([0, 17, 1499])
+    out, nv = farthest_point_sample_masked(pc.to(dev), mask.to(dev), n_out, start.to(dev))
+    torch.cuda.synchronize()
+    assert nv.cpu().tolist() == mask.sum(-1).tolist()
+    for b in range(B):
+        valid = pc[b][:, mask[b]].T[None].contiguous()
+        pts, _ = ref_fps(valid, K=n_out, start_idx=start[b:b + 1])
+        assert torch.equal(out[b].cpu(), pts[0].T), f"instance {b}"
