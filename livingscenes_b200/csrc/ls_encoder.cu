@@ -505,7 +505,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             LS_CHECK_LAUNCH("k_knn_small");
             ea.idx_in = p.small_idx;
         }
-        if (ea.idx_in == nullptr && g_use_knn_tc) {
+        if (ea.idx_in == nullptr && g_use_knn_tc && Ns <= 65535) {  // candidate indices are 16-bit; larger sets: brute force
             // tensor-core candidate filter + exact re-rank instead of the brute-force phase 1
             std::unique_ptr<ProfScope> ps(new ProfScope(7, i, st));
             const int D = Ci * 3;
