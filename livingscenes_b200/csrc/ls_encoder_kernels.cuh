@@ -1270,7 +1270,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArg
         }
         if (lane < LS_KNN_K) {
             const size_t o = ((size_t)b * a.Nd + q) * LS_KNN_K + lane;
-            const int64_t sv = min(s_out, a.Ns - 1);
+            const int64_t sv = max(0, min(s_out, a.Ns - 1));  // stay in bounds on NaN input (empty candidate list)
             a.idx_out[o] = sv;
             if (a.idx_tap) a.idx_tap[o] = sv;
             if (a.dist_out) a.dist_out[o] = d_out;
