@@ -46,17 +46,17 @@ DOWN = {2: 2, 4: 4, 5: 4}
 
 
 def load_state_dict():
-    from oracle import restatement as R  # only for the seeded stand-in weights / synthetic clouds
+    from livingscenes_b200 import synthetic as S
 
     if os.path.exists(SHIPPED):
         return torch.load(SHIPPED, map_location="cpu", weights_only=True), "shipped checkpoint weights"
-    return R.random_state_dict(0), "seeded random weights (shipped checkpoint not present)"
+    return S.random_state_dict(0), "seeded random weights (shipped checkpoint not present)"
 
 
 def make_scene_batch(n_pairs: int, seed: int):
     """[n_pairs*64, 3, 1024]: per pair 32 ref instances then 32 rescan instances = permuted, rotated,
     translated, re-noised copies of the ref ones (SURVEY.md 8d, config C3 at N=1024)."""
-    from oracle import restatement as R
+    from livingscenes_b200 import synthetic as R
 
     g = torch.Generator().manual_seed(seed)
     out, perms = [], []
@@ -167,15 +167,15 @@ def cpu_path_step(sd, x_pair, use_reference_modules):
 
 
 def cpu_setup(sample_inst: int):
-    from oracle import p3d_shim, ref_loader
-    from oracle import restatement as R
+    from livingscenes_b200 import synthetic as S
+    from oracle import p3d_shim, ref_loader  # the CPU-baseline leg is the one place bench.py executes oracle/
 
     p3d_shim.EXACT = False  # timing leg: cheapest honest fp32 kNN instead of the fp64 parity kNN
     torch.set_num_threads(os.cpu_count() or 1)
     sd, wdesc = load_state_dict()
     half = sample_inst // 2
-    ref = R.synth_instances(half, N_POINTS, 777)
-    res = R.random_rotations(half, 778) @ ref.flip(0) + 0.1
+    ref = S.synth_instances(half, N_POINTS, 777)
+    res = S.random_rotations(half, 778) @ ref.flip(0) + 0.1
     x = torch.cat([ref, res], 0)
     mods, kind = None, "port"
     if ref_loader.available() and ref_loader.checkpoint_available():

@@ -15,7 +15,7 @@
 //            error measured for this product);
 //   * 16 sources have d <= T + |q|^2 + E, hence every member of the exact top-16 has dt <= T + 2E <= tau + 2E:
 //            the candidate set {dt <= tau + 2E} CONTAINS the exact answer; ~22 candidates per query on the
-//            shipped model (scripts/emulate_tc_knn.py), the exact re-rank then decides order and ties.
+//            shipped model (tests/study_tc_knn_filter.py), the exact re-rank then decides order and ties.
 //   * a query whose list overflows is flagged (count -1) and brute-forced exactly by the consumer.
 //
 // k_knn_pack   features [B][D][N] -> per (128-point tile, 8-dim k-block) the canonical UMMA shared-memory

@@ -318,79 +318,7 @@ def sdf_decode(Wd, query: torch.Tensor, code: dict, latent_in=(4,)) -> torch.Ten
     return torch.tanh(h).reshape(B, M)
 
 
-# --------------------------------------------------------------------------- weights
-def random_state_dict(seed: int = 0, cfg: Optional[dict] = None) -> Dict[str, torch.Tensor]:
-    """Seeded stand-in weights with the shipped checkpoint's keys and shapes
-    (kaiming_uniform(a=sqrt 5) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)), vec_layers.py:117)."""
-    cfg = dict(SHIPPED_ENCODER_CFG, **(cfg or {}))
-    g = torch.Generator().manual_seed(seed)
-    sd: Dict[str, torch.Tensor] = {}
-
-    def uni(name, out_c, in_c, fan_in=None):
-        bnd = 1.0 / math.sqrt(fan_in or in_c)
-        sd[name] = (torch.rand(out_c, in_c, generator=g) * 2 - 1) * bnd
-
-    def lna(prefix, cin, cout, shared=False):
-        uni(prefix + ".lin.weight", cout, cin)
-        uni(prefix + ".act.lin_dir.weight", 1 if shared else cout, cout)
-
-    fd = cfg["feat_dim"]
-    for i in range(cfg["num_layers"]):
-        cin = 3 if i == 0 else 2 * fd[i - 1]
-        lna(f"encoder.V_list.{i}", cin, fd[i])
-        if i >= cfg["atten_start_layer"]:
-            lna(f"encoder.K_list.{i}", cin, fd[i])
-            lna(f"encoder.Q_list.{i}", fd[i - 1], fd[i])
-        if cfg["use_res_global_conv"] and i >= cfg["res_global_start_layer"]:
-            lna(f"encoder.global_conv_list.{i - cfg['res_global_start_layer']}", 2 * fd[i], fd[i])
-    c = cfg["c_dim"]
-    lna("encoder.conv_c", fd[-1], c, shared=True)
-    uni("encoder.fc_inv.weight", c, c)
-    lna("encoder.fc_center.fc0", c, c // 2)
-    uni("encoder.fc_center.lin1.weight", 1, c // 2)
-    uni("encoder.fc_center.act2.lin_dir.weight", 1, 1)
-    uni("encoder.fc_center.shortcut.weight", 1, c)
-    dims = [513, 768, 768, 768, 255, 768, 768, 768, 768, 1]
-    ins = [513, 768, 768, 768, 768, 768, 768, 768, 768]
-    for l in range(9):
-        o, i_ = dims[l + 1], ins[l]
-        bnd = 1.0 / math.sqrt(i_)
-        v = (torch.rand(o, i_, generator=g) * 2 - 1) * bnd
-        bias = (torch.rand(o, generator=g) * 2 - 1) * bnd
-        if l < 8:
-            sd[f"decoder.lin{l}.bias"] = bias
-            # a non-trivial gain so that weight-norm folding is actually exercised
-            sd[f"decoder.lin{l}.weight_g"] = v.norm(dim=1, keepdim=True) * (0.75 + 0.5 * torch.rand(o, 1, generator=g))
-            sd[f"decoder.lin{l}.weight_v"] = v
-        else:
-            sd[f"decoder.lin{l}.weight"] = v
-            sd[f"decoder.lin{l}.bias"] = bias
-    return sd
-
-
-# --------------------------------------------------------------------------- synthetic inputs
-def synth_instances(B: int, N: int, seed: int) -> torch.Tensor:
-    """SURVEY.md section 8d synthetic clouds: noisy ellipsoidal shells, [B,3,N] fp32.
-    Directions uniform on S^2, radii 0.3 + 0.2 U(0,1), per-axis scale (1.0, 0.6, 0.8) times a
-    per-instance factor U(0.5, 1.5), N(0, 0.005^2) noise, translation U(-2, 2)^3."""
-    g = torch.Generator().manual_seed(seed)
-    d = torch.randn(B, N, 3, generator=g)
-    d = d / d.norm(dim=-1, keepdim=True).clamp_min(1e-9)
-    r = 0.3 + 0.2 * torch.rand(B, N, 1, generator=g)
-    ax = torch.tensor([1.0, 0.6, 0.8])[None, None, :]
-    sc = 0.5 + torch.rand(B, 1, 1, generator=g)
-    # a few low-frequency bumps so instances are distinguishable by shape
-    bump = 1.0 + 0.25 * torch.sin(3.0 * d[..., :1] + 6.28 * torch.rand(B, 1, 1, generator=g)) \
-        * torch.cos(2.0 * d[..., 1:2] + 6.28 * torch.rand(B, 1, 1, generator=g))
-    p = d * r * ax * sc * bump + 0.005 * torch.randn(B, N, 3, generator=g)
-    p = p + (torch.rand(B, 1, 3, generator=g) * 4 - 2)
-    return p.transpose(1, 2).contiguous().float()
-
-
-def random_rotations(B: int, seed: int) -> torch.Tensor:
-    g = torch.Generator().manual_seed(seed)
-    A = torch.randn(B, 3, 3, generator=g, dtype=torch.float64)
-    Q, R = torch.linalg.qr(A)
-    Q = Q * torch.sign(torch.diagonal(R, dim1=1, dim2=2))[:, None, :]
-    Q[:, :, 0] *= torch.det(Q)[:, None]
-    return Q.float()
+# --------------------------------------------------------------------------- synthetic inputs / weights
+# The seeded generators live in the package (livingscenes_b200/synthetic.py: pure-torch CPU helpers shared by
+# bench.py, scripts/ and the tests) so that nothing outside tests / smoke / the CPU-baseline leg imports oracle/.
+from livingscenes_b200.synthetic import random_rotations, random_state_dict, synth_instances  # noqa: E402,F401

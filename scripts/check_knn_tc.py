@@ -12,7 +12,7 @@ sd, _ = bench.load_state_dict()
 model = ls.Shape_Prior.from_state_dict(sd).to(dev).eval()
 enc = model.encoder
 for (B, N) in ((2, 512), (8, 1024), (3, 2048), (5, 1000), (256, 1024)):
-    from oracle import restatement as R
+    from livingscenes_b200 import synthetic as R
     x = R.synth_instances(B, N, 99 + B).to(dev)
     outs = {}
     for name, on, ks in (("exact", False, 1.0), ("tc", True, 1.0), ("tc_overflow", True, 1e6)):

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import livingscenes_b200 as ls
 from livingscenes_b200 import _lib
-from oracle import restatement as R
+from livingscenes_b200 import synthetic as R
 
 dev = torch.device("cuda:0")
 SHIPPED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "livingscenes_b200", "_weights", "shipped_fp32.pt")
