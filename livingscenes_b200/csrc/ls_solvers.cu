@@ -62,7 +62,8 @@ __device__ void normalize_and_score(const float* z0, const float* z1, int n, int
         const float* a = an + (size_t)i * dim;
         const float* b = bn + (size_t)j * dim;
         float acc = 0.f;
-        for (int d = 0; d < dim; ++d) acc = fmaf(a[d], b[d], acc);
+#pragma unroll 8
+        for (int d = 0; d < dim; ++d) acc = fmaf(a[d], b[d], acc);  // loads run ahead, the FMA order is fixed
         S[e] = acc;
     }
     __syncthreads();
@@ -94,6 +95,50 @@ __global__ void __launch_bounds__(1024) k_seq_match(const float* __restrict__ z0
     if (n == 0 || m == 0) return;
     normalize_and_score(z0 + (size_t)o0 * dim, z1 + (size_t)o1 * dim, n, m, dim, an, bn, S);
     const int rounds = min(n, m);
+    if (n <= 32 && m <= 32) {
+        // Small scenes (the common case: <= 32 instances per scan): one warp holds the whole score matrix in
+        // registers (lane = row) and replays the same fp32 sequence without block-wide barriers -- the general
+        // path below spends its time in 3 block reductions per round.
+        if (threadIdx.x >= 32) return;
+        const int lane = threadIdx.x;
+        float s[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = (lane < n && j < m) ? S[lane * m + j] : 0.f;
+        bool row_alive = lane < n;
+        unsigned col_alive = m == 32 ? 0xffffffffu : ((1u << m) - 1u);
+        for (int r = 0; r < rounds; ++r) {
+            float mx = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (row_alive && ((col_alive >> j) & 1u)) mx = fmaxf(mx, s[j]);
+            mx = warp_max(mx);
+            const float den = mx + 1e-5f;
+            float mx2 = -FLT_MAX;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (row_alive && ((col_alive >> j) & 1u)) {
+                    s[j] = s[j] / den;
+                    mx2 = fmaxf(mx2, s[j]);
+                }
+            }
+            mx2 = warp_max(mx2);
+            int first = 0x7fffffff;
+#pragma unroll
+            for (int j = 31; j >= 0; --j)
+                if (row_alive && ((col_alive >> j) & 1u) && s[j] == mx2) first = lane * m + j;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(FULL, first, o));
+            if (first == 0x7fffffff) break;  // NaN scores: nothing compares equal; leave the rest unmatched
+            const int bi = first / m, bj = first - bi * m;
+            if (lane == 0) {
+                m0[o0 + bi] = bj;
+                m1[o1 + bj] = bi;
+            }
+            if (lane == bi) row_alive = false;
+            col_alive &= ~(1u << bj);
+        }
+        return;
+    }
     for (int r = 0; r < rounds; ++r) {
         float mx = -FLT_MAX;
         for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
@@ -622,7 +667,9 @@ int run_match(const float* z0, const float* z1, int dim, const int32_t* off0, co
             return LS_ERR_WORKSPACE;
         }
         ws_off = ws_end;
-        const int threads = max_nm <= 4096 ? 256 : 1024;
+        // small pairs: one score per thread (the greedy rounds then run in a single warp); mid-size pairs keep the
+        // block reductions of the greedy loop cheap with 8 warps
+        const int threads = max_nm <= 1024 ? 1024 : (max_nm <= 4096 ? 256 : 1024);
         if (SEQ) {
                 k_seq_match<<<count, threads, (size_t)max_npm + 16, st>>>(z0, z1, dim, tab, static_cast<float*>(ws), m0, m1);
                 LS_CHECK_LAUNCH("k_seq_match");
