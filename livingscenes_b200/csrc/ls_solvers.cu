@@ -43,10 +43,15 @@ __device__ __forceinline__ int block_min_int(int v, int* red) {
     return r;
 }
 
-// rows / max(|row|, 1e-12) (F.normalize, matcher_new.py:110-111) and S = A B^T (:120)
+// rows / max(|row|, 1e-12) (F.normalize, matcher_new.py:110-111) and S = A B^T (:120).
+// ``stage`` (optional shared memory, n*dim + dim*33 floats, only for n, m <= 32): the normalised rows are kept in
+// shared memory -- A row-major (broadcast reads), B transposed with a padded stride (conflict-free) -- instead of
+// being re-read from global memory with 32 scattered sectors per load; the FMA order over d is the same.
 __device__ void normalize_and_score(const float* z0, const float* z1, int n, int m, int dim, float* an,
-                                    float* bn, float* S) {
+                                    float* bn, float* S, float* stage = nullptr) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* sA = stage;
+    float* sBt = stage ? stage + (size_t)n * dim : nullptr;
     for (int r = w; r < n + m; r += nw) {
         const float* src = r < n ? z0 + (size_t)r * dim : z1 + (size_t)(r - n) * dim;
         float* dst = r < n ? an + (size_t)r * dim : bn + (size_t)(r - n) * dim;
@@ -54,16 +59,31 @@ __device__ void normalize_and_score(const float* z0, const float* z1, int n, int
         for (int d = lane; d < dim; d += 32) s = fmaf(src[d], src[d], s);
         s = warp_sum(s);
         const float den = fmaxf(sqrtf(s), EPS_NRM);
-        for (int d = lane; d < dim; d += 32) dst[d] = src[d] / den;
+        for (int d = lane; d < dim; d += 32) {
+            const float v = src[d] / den;
+            if (stage) {
+                if (r < n) sA[(size_t)r * dim + d] = v;
+                else sBt[(size_t)d * 33 + (r - n)] = v;
+            } else {
+                dst[d] = v;
+            }
+        }
     }
     __syncthreads();
     for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
         const int i = e / m, j = e - i * m;
-        const float* a = an + (size_t)i * dim;
-        const float* b = bn + (size_t)j * dim;
         float acc = 0.f;
+        if (stage) {
+            const float* a = sA + (size_t)i * dim;
+            const float* b = sBt + j;
 #pragma unroll 8
-        for (int d = 0; d < dim; ++d) acc = fmaf(a[d], b[d], acc);  // loads run ahead, the FMA order is fixed
+            for (int d = 0; d < dim; ++d) acc = fmaf(a[d], b[(size_t)d * 33], acc);
+        } else {
+            const float* a = an + (size_t)i * dim;
+            const float* b = bn + (size_t)j * dim;
+#pragma unroll 8
+            for (int d = 0; d < dim; ++d) acc = fmaf(a[d], b[d], acc);  // loads run ahead, the FMA order is fixed
+        }
         S[e] = acc;
     }
     __syncthreads();
@@ -74,7 +94,8 @@ __device__ void normalize_and_score(const float* z0, const float* z1, int n, int
 // new max, record the pair, retire its row and column.
 __global__ void __launch_bounds__(1024) k_seq_match(const float* __restrict__ z0, const float* __restrict__ z1,
                                                     int dim, const PairTable tab, float* __restrict__ wsf,
-                                                    int64_t* __restrict__ m0, int64_t* __restrict__ m1) {
+                                                    int64_t* __restrict__ m0, int64_t* __restrict__ m1, int stage_off,
+                                                    int stage_floats) {
     __shared__ float redf[32];
     __shared__ int redi[32];
     extern __shared__ unsigned char alive[];  // [n] rows then [m] cols
@@ -93,7 +114,11 @@ __global__ void __launch_bounds__(1024) k_seq_match(const float* __restrict__ z0
         m1[o1 + j] = -1;
     }
     if (n == 0 || m == 0) return;
-    normalize_and_score(z0 + (size_t)o0 * dim, z1 + (size_t)o1 * dim, n, m, dim, an, bn, S);
+    // small pairs: the launcher provides shared memory for the normalised rows behind the alive flags
+    float* stage = (stage_floats > 0 && n <= 32 && m <= 32 && (size_t)n * dim + (size_t)dim * 33 <= (size_t)stage_floats)
+                       ? reinterpret_cast<float*>(alive + stage_off)
+                       : nullptr;
+    normalize_and_score(z0 + (size_t)o0 * dim, z1 + (size_t)o1 * dim, n, m, dim, an, bn, S, stage);
     const int rounds = min(n, m);
     if (n <= 32 && m <= 32) {
         // Small scenes (the common case: <= 32 instances per scan): one warp holds the whole score matrix in
@@ -671,8 +696,20 @@ int run_match(const float* z0, const float* z1, int dim, const int32_t* off0, co
         // block reductions of the greedy loop cheap with 8 warps
         const int threads = max_nm <= 1024 ? 1024 : (max_nm <= 4096 ? 256 : 1024);
         if (SEQ) {
-                k_seq_match<<<count, threads, (size_t)max_npm + 16, st>>>(z0, z1, dim, tab, static_cast<float*>(ws), m0, m1);
-                LS_CHECK_LAUNCH("k_seq_match");
+            // alive flags, then (small pairs only) the shared-memory stage of the normalised rows
+            const int stage_off = (max_npm + 16 + 15) & ~15;
+            int stage_floats = 0;
+            if (max_nm <= 1024 && max_npm <= 64) stage_floats = 32 * dim + dim * 33;
+            size_t smem = (size_t)stage_off + (size_t)stage_floats * sizeof(float);
+            if (smem > 200 * 1024) {
+                stage_floats = 0;
+                smem = (size_t)stage_off;
+            }
+            if (smem > 48 * 1024)
+                LS_CHECK_CUDA(cudaFuncSetAttribute(k_seq_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_seq_match<<<count, threads, smem, st>>>(z0, z1, dim, tab, static_cast<float*>(ws), m0, m1, stage_off,
+                                                      stage_floats);
+            LS_CHECK_LAUNCH("k_seq_match");
         } else {
             const size_t smem = (size_t)max_npm * sizeof(int) + 16;
             if (smem > 48 * 1024)
