@@ -263,6 +263,18 @@ int pick_qpc(int B, int Nd, bool phase2_only, int Co = 0, size_t table_bytes = 0
     return qpc;
 }
 
+int launch_rerank(const RerankArgs& ra, int B, cudaStream_t st) {
+    const dim3 grid((ra.Nd + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B);
+    switch (ra.Dp) {
+        case 8: k_knn_rerank<8><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        case 96: k_knn_rerank<96><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        case 192: k_knn_rerank<192><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        default: k_knn_rerank<0><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+    }
+    LS_CHECK_LAUNCH("k_knn_rerank");
+    return LS_OK;
+}
+
 int launch_edge(int mode, const EdgeArgs& a, cudaStream_t st) {
     LS_REQUIRE(a.qpc >= 8 && a.qpc <= QT && a.qpc % 8 == 0, "bad qpc");
     dim3 grid((a.Nd + a.qpc - 1) / a.qpc, a.B);
@@ -549,8 +561,8 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ra.Dp = ka.n_kb * KT_KB;
             ra.idx_out = p.kidx;
             ra.idx_tap = io->knn_idx[i];
-            k_knn_rerank<<<dim3((Nd + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B), RR_WARPS * 32, 0, st>>>(ra);
-            LS_CHECK_LAUNCH("k_knn_rerank");
+            rc = launch_rerank(ra, B, st);
+            if (rc != LS_OK) return rc;
             ea.idx_in = p.kidx;
             ea.idx_out = nullptr;
         }
@@ -793,9 +805,7 @@ int ls_knn_tc(const float* query, const float* source, int32_t B, int32_t D, int
     ra.Dp = ka.n_kb * KT_KB;
     ra.idx_out = idx;
     ra.dist_out = dist2;
-    k_knn_rerank<<<dim3((Nq + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B), RR_WARPS * 32, 0, st>>>(ra);
-    LS_CHECK_LAUNCH("k_knn_rerank");
-    return LS_OK;
+    return launch_rerank(ra, B, st);
 }
 
 int ls_fps_workspace_bytes(int32_t B, int32_t N, size_t* bytes) {

@@ -1200,7 +1200,11 @@ __device__ __forceinline__ unsigned ord_f32(float f) {  // order-preserving map 
     const unsigned u = __float_as_uint(f);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+// DP > 0: the padded feature dimension is a compile-time constant (8 / 96 / 192 on the shipped model): the row
+// loops unroll and the row addresses become constant strides; DP == 0 reads it from the arguments.
+template <int DP>
 __global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArgs a) {
+    const int Dp = DP > 0 ? DP : a.Dp;
     __shared__ __align__(16) float sq_all[RR_WARPS][4 * RR_F4];
     __shared__ u64 ssort[RR_WARPS][64];
     __shared__ __align__(16) float scoop[RR_WARPS][(1 + RR_NR) * RR_ROW];
@@ -1208,7 +1212,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArg
     const int b = blockIdx.y, qbase = (blockIdx.x * RR_WARPS + w) * RR_QPW;
     if (qbase >= a.Nd) return;
     const int n_pt_q = (a.Nd + KT_PTS - 1) / KT_PTS;
-    const float* pms = a.pm_s + (size_t)b * a.Ns * a.Dp;
+    const float* pms = a.pm_s + (size_t)b * a.Ns * Dp;
     float* sq = sq_all[w];
     // software pipeline over the warp's queries: the next query's list is in flight while this one is processed
     int c_n, ci_n;
@@ -1230,16 +1234,16 @@ __global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArg
         const int c_j = c_n, ci_j = ci_n;
         const float cd_j = cd_n, e2_j = e2_n;
         if (j + 1 < RR_QPW) load_list(q + 1);
-        const float* qrow = a.pm_q + ((size_t)b * a.Nd + q) * a.Dp;
+        const float* qrow = a.pm_q + ((size_t)b * a.Nd + q) * Dp;
         int s_out;
         float d_out = 0.f;
         if (c_j < 0) {
-            const u64 lk = knn_bruteforce_pm(qrow, sq, pms, a.Ns, a.Dp);
+            const u64 lk = knn_bruteforce_pm(qrow, sq, pms, a.Ns, Dp);
             s_out = key_idx(lk) & 0x7fffffff;
             d_out = key_dist(lk);
         } else if (c_j > 32 || a.all_exact) {
             const int qt = q / KT_PTS;
-            const u64 lk = knn_rerank(qrow, sq, pms, a.cand + ((size_t)b * n_pt_q + qt) * KT_CAP * KT_PTS + q % KT_PTS, c_j, a.Dp);
+            const u64 lk = knn_rerank(qrow, sq, pms, a.cand + ((size_t)b * n_pt_q + qt) * KT_CAP * KT_PTS + q % KT_PTS, c_j, Dp);
             s_out = key_idx(lk) & 0x7fffffff;
             d_out = key_dist(lk);
         } else {
@@ -1261,7 +1265,7 @@ __global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArg
             const bool need = lane < cnt && (adj || prev_adj) && rs <= LS_KNN_K - 1;
             s_out = s;
             if (__any_sync(FULL, need)) {
-                const float d = exact_dist_coop(need, s, qrow, pms, a.Dp, scoop[w]);
+                const float d = exact_dist_coop(need, s, qrow, pms, Dp, scoop[w]);
                 // final order: by run (runs are contiguous rank ranges), inside a re-sorted run by (exact d, index)
                 u64 k2 = lane < cnt ? (((u64)(unsigned)rs << 58) | ((u64)(need ? __float_as_uint(d) : 0u) << 26) | (unsigned)s) : KEY_MAX;
                 k2 = warp_rank_sort(k2, cnt, ssort[w]);
