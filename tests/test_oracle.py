@@ -129,3 +129,59 @@ def test_tensor_core_knn_argument_on_cpu():
     assert idx[7, :3].tolist() == [7, 40, 300]
     assert st["candidates_max"] <= 56 and st["candidates_mean"] < 30, st
     assert st["exact_per_query_mean"] < 8, st
+
+
+def test_icp_restatement_is_consistent():
+    """The restated pytorch3d ICP (oracle/p3d_shim.py; parity unpinned -- pytorch3d is not vendored) recovers a
+    planted rigid motion exactly on noise-free subsets, its alignment step agrees with the restated Kabsch
+    (pose_estimation.py, column-vector convention) and its rmse sequence is non-increasing."""
+    import math
+
+    import torch
+
+    from oracle import p3d_shim
+    from oracle import restatement as R
+
+    g = torch.Generator().manual_seed(3)
+    Y = torch.randn(2, 600, 3, generator=g)
+    a = 0.15
+    Rz = torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]])
+    t = torch.tensor([0.03, -0.02, 0.05])
+    X = (Y[:, :400] - t) @ Rz  # so that X Rz^T + t == Y[:, :400]
+    sol = p3d_shim.iterative_closest_point(X, Y)
+    assert sol.converged
+    assert float((sol.RTs.R - Rz.T).abs().max()) < 1e-5 and float((sol.RTs.T - t).abs().max()) < 1e-5
+    assert float(sol.rmse.max()) < 1e-5
+    # one alignment step == Kabsch with uniform weights (transpose: row- vs column-vector convention)
+    al = p3d_shim.corresponding_points_alignment(X, Y[:, :400])
+    Rk, tk, _ = R.kabsch(X, Y[:, :400])
+    assert float((al.R.transpose(1, 2) - Rk).abs().max()) < 1e-5
+    assert float((al.T - tk.squeeze(2)).abs().max()) < 1e-5
+    # monotone rmse on a noisy problem
+    Xn = X + 0.01 * torch.randn(X.shape, generator=g)
+    prev = None
+    for it in (1, 2, 4, 8, 16):
+        r = p3d_shim.iterative_closest_point(Xn, Y, max_iterations=it).rmse
+        if prev is not None:
+            assert bool((r <= prev + 1e-7).all())
+        prev = r
+
+
+def test_fps_restatement_start_index_and_coverage():
+    """Oracle FPS with a chosen first index: the first sample is that index, samples are distinct and the
+    covering radius does not increase when more points are sampled (the defining property of FPS)."""
+    import torch
+
+    from oracle.p3d_shim import sample_farthest_points
+
+    g = torch.Generator().manual_seed(4)
+    pts = torch.rand(2, 500, 3, generator=g)
+    start = torch.tensor([7, 499])
+    radius = []
+    for K in (16, 64, 256):
+        sub, idx = sample_farthest_points(pts, K=K, start_idx=start)
+        assert idx[:, 0].tolist() == start.tolist()
+        assert all(len(set(r.tolist())) == K for r in idx)
+        d = torch.cdist(pts, sub).min(-1).values.max(-1).values  # covering radius per cloud
+        radius.append(d)
+    assert bool((radius[1] <= radius[0]).all()) and bool((radius[2] <= radius[1]).all())
