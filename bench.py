@@ -187,29 +187,39 @@ def cpu_setup(sample_inst: int):
     return sd, x, mods, kind, wdesc
 
 
+WORKLOAD = ("BASELINE config[1]: 256 synthetic instances x 1024 points per GPU = 4 scene pairs x "
+            "(32 ref + 32 rescan); Shape_Prior.encode + sequential_matcher + Kabsch per matched pair")
+
+
 def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (its own modules where /root/reference is
+    mounted, else the oracle port) on all host threads.  One step = one bounded sample of the workload (a scene
+    pair of 2+2 instances, ~3.6 s on 16 cores; 1+1 when K > 40) so that K steps end within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
+    steps = max(1, min(args.steps, 60))
+    sample = 4 if steps <= 40 else 2
     sd, x, mods, kind, wdesc = cpu_setup(sample)
-    for _ in range(max(1, min(args.warmup, 1))):  # bounded: one warm-up pass is enough on the CPU
+    warm = max(1, min(args.warmup, 2))
+    for _ in range(warm):
         cpu_path_step(sd, x, mods)
-    steps = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(steps):
         cpu_path_step(sd, x, mods)
     dt = (time.perf_counter() - t0) / steps
     val = sample / dt
     cores = torch.get_num_threads()
-    sample_desc = f"{sample} instances of {N_POINTS} points per step (1 scene pair of {sample // 2}+{sample // 2}), {steps} timed steps"
+    sample_desc = (f"{sample} instances of {N_POINTS} points per step (1 scene pair of {sample // 2}+{sample // 2}), "
+                   f"{steps} timed steps after {warm} warm-up")
     print(json.dumps({
         "impl": "reference", "metric": "instances/sec (N=1024 pts) encode+match+pose", "value": val,
-        "unit": "instances/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3,
+        "unit": "instances/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": f"synthetic ({wdesc})",
-        "config": {"workload": "bounded CPU sample of the b200 arm's workload (256 instances x 1024 points per GPU: "
-                               "4 scene pairs x (32+32), encode + sequential match + Kabsch)", "n_points": N_POINTS},
+        "config": {"workload": WORKLOAD, "instances_per_gpu": INST_PER_GPU, "n_points": N_POINTS,
+                   "pairs_per_gpu": PAIRS_PER_GPU, "sample": sample_desc,
+                   "parallelism": f"host CPU, {cores} threads (rank 0 only)"},
         "cpu_baseline": {"value": val, "unit": "instances/s", "cores": cores, "kind": kind, "sample": sample_desc},
         "e2e": {"value": val, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -424,8 +434,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": f"synthetic ({wdesc})",
-            "config": {"workload": "BASELINE config[1]: 256 synthetic instances x 1024 points per GPU = 4 scene pairs x "
-                                   "(32 ref + 32 rescan); Shape_Prior.encode + sequential_matcher + Kabsch per matched pair",
+            "config": {"workload": WORKLOAD,
                        "instances_per_gpu": INST_PER_GPU, "n_points": N_POINTS, "pairs_per_gpu": PAIRS_PER_GPU,
                        "parallelism": f"instance-sharded x{world}" + (" + 1 NCCL all-gather of packed codes" if world > 1 else ""),
                        "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set ~2 GB >> 126 MB L2",
