@@ -158,6 +158,14 @@ LS_API int ls_set_knn_tensor_cores(int32_t on, float kappa_scale);
  * side stream next to the kNN chain (fork/join with events; capturable).  0: everything on the caller's stream. */
 LS_API int ls_set_overlap(int32_t on);
 LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 path where packed weights exist */
+/* 2 (default): persistent warp-specialised tcgen05 GEMM (bulk-TMA fed, double-buffered TMEM); 1: the round-1
+ * one-CTA-per-tile kernel (kept for A/B measurements).  Process-global, like the other ls_set_* switches. */
+LS_API int ls_set_gemm_variant(int32_t variant);
+/* Table bytes per wave of the per-layer {point-level table GEMMs -> EdgeConv} schedule (default 28 MiB, env LS_WAVE_MB):
+ * a layer's batch is processed in waves of that many bytes of gather tables, two table slots alternating, so that
+ * the tables are consumed out of L2 instead of HBM.  0: one launch per layer for the whole batch.  Results do not
+ * depend on the setting. */
+LS_API int ls_set_wave_bytes(int64_t bytes);
 
 /* ------------------------------------------------------------------------------------------
  * Stand-alone graph ops (the pytorch3d boundary of the reference)

@@ -79,6 +79,8 @@ _PROTOS = {
     "ls_vn_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_int32, C.c_int32, C.c_void_p]),
     "ls_set_tensor_cores": (C.c_int, [C.c_int32]),
+    "ls_set_gemm_variant": (C.c_int, [C.c_int32]),
+    "ls_set_wave_bytes": (C.c_int, [C.c_int64]),
     "ls_set_overlap": (C.c_int, [C.c_int32]),
     "ls_set_knn_tensor_cores": (C.c_int, [C.c_int32, C.c_float]),
     "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -164,7 +166,7 @@ def profile_enable(on: bool) -> None:
 
 def profile_read():
     """[(stage_name, layer, ms)] of the last encoder forward (synchronise the stream first)."""
-    n = 64
+    n = 8192  # wave scheduling issues a stage once per wave
     st, ly, ms, cnt = (C.c_int32 * n)(), (C.c_int32 * n)(), (C.c_float * n)(), C.c_int32(0)
     check(lib().ls_profile_read(st, ly, ms, n, C.byref(cnt)), "ls_profile_read")
     return [(STAGE_NAMES[st[i]], int(ly[i]), float(ms[i])) for i in range(cnt.value)]
@@ -177,6 +179,16 @@ def kernel_launches() -> int:
 def set_tensor_cores(on: bool) -> None:
     """Route the packed-weight GEMMs through the tcgen05 3xTF32 kernel (default) or the FP32 SIMT kernel."""
     check(lib().ls_set_tensor_cores(int(on)), "ls_set_tensor_cores")
+
+
+def set_gemm_variant(variant: int) -> None:
+    """2 (default): persistent warp-specialised tcgen05 GEMM; 1: the round-1 one-CTA-per-tile kernel."""
+    check(lib().ls_set_gemm_variant(int(variant)), "ls_set_gemm_variant")
+
+
+def set_wave_bytes(nbytes: int) -> None:
+    """Table bytes per wave of the {table GEMM -> EdgeConv} schedule (0: whole batch per launch, as in round 1)."""
+    check(lib().ls_set_wave_bytes(int(nbytes)), "ls_set_wave_bytes")
 
 
 def set_overlap(on: bool) -> None:

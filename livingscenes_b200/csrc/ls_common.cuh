@@ -131,5 +131,6 @@ int tc_pack_weights(const float* W, int R, int K, int ldw, float* packed, cudaSt
 bool gemm_tc_supported(const GemmArgs& a);
 int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st);
 extern bool g_use_tensor_cores;
+extern int g_gemm_variant;  // 2 = persistent warp-specialised k_gemm_tc2 (default), 1 = round-1 k_gemm_tc
 
 }  // namespace ls

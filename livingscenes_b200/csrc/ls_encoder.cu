@@ -51,31 +51,42 @@ struct ProfScope {
 //      events recorded in the capturing stream pull the side stream into the capture as a parallel branch).
 struct SideCtx {
     int dev = -1;
-    cudaStream_t s = nullptr;
-    cudaEvent_t fork_ev = nullptr, join_fps = nullptr, join_tab = nullptr;
+    cudaStream_t s_fps = nullptr, s_tab = nullptr;  // FPS chain / point-level table GEMMs
+    cudaEvent_t fork_ev = nullptr, join_fps = nullptr, ev_tab[2] = {nullptr, nullptr}, ev_edge[2] = {nullptr, nullptr};
     bool ok = false;
+    void destroy() {
+        if (s_fps) cudaStreamDestroy(s_fps);
+        if (s_tab) cudaStreamDestroy(s_tab);
+        for (cudaEvent_t e : {fork_ev, join_fps, ev_tab[0], ev_tab[1], ev_edge[0], ev_edge[1]})
+            if (e) cudaEventDestroy(e);
+        *this = SideCtx();
+    }
 };
-static thread_local SideCtx g_side;
+constexpr int MAX_SIDE_DEVICES = 16;
+static thread_local SideCtx g_side[MAX_SIDE_DEVICES];  // one context per (thread, device): nothing leaks when a thread alternates devices
 static bool g_overlap = true;
 
 static SideCtx* side_ctx(cudaStream_t main_stream) {
     if (!g_overlap || g_prof_on) return nullptr;  // per-stage event timing needs the serial order
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (g_side.ok && g_side.dev == dev) return &g_side;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_SIDE_DEVICES) return nullptr;
+    SideCtx& c = g_side[dev];
+    if (c.ok) return &c;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(main_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
         return nullptr;  // resources are only created outside a capture; this call runs serially
-    SideCtx c;
     c.dev = dev;
-    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&c.fork_ev, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.join_fps, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.join_tab, cudaEventDisableTiming) != cudaSuccess)
+    bool good = cudaStreamCreateWithFlags(&c.s_fps, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&c.s_tab, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[] = {&c.fork_ev, &c.join_fps, &c.ev_tab[0], &c.ev_tab[1], &c.ev_edge[0], &c.ev_edge[1]};
+    for (cudaEvent_t* e : evs) good = good && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    if (!good) {
+        c.destroy();  // nothing half-created is kept
+        cudaGetLastError();
         return nullptr;
+    }
     c.ok = true;
-    g_side = c;
-    return &g_side;
+    return &c;
 }
 
 namespace {
@@ -102,6 +113,15 @@ int small_tc_min() {
     }();
     return v;
 }
+// Wave scheduling of {table GEMMs -> EdgeConv}: the point-level gather tables of a layer are 1.6-5.5 MB per instance
+// (19.5 MB over the six layers).  Written for the whole batch they leave L2 long before the EdgeConv reads them back
+// (round 1: 4.96 GB written + ~6 GB re-read per 256-instance step).  A wave is as many instances as fit g_wave_bytes
+// of tables; two table slots alternate, so the GEMM of wave w+1 overlaps the EdgeConv of wave w and the slot lines
+// are overwritten while still dirty in the 126 MB L2 instead of travelling to HBM and back.  0 disables.
+long long g_wave_bytes = [] {
+    const char* e = getenv("LS_WAVE_MB");
+    return (long long)(e ? atof(e) : 28.0) * (1LL << 20);
+}();
 bool g_use_knn_tc = true;      // tensor-core candidate filter for the larger source sets
 float g_knn_tc_kappa_scale = 1.f;
 
@@ -247,13 +267,15 @@ int launch_edge_cpl(const EdgeArgs& a, int cpl, dim3 grid, cudaStream_t st) {
 // points per CTA layers 2-4 had 55-220 instances (0.3-1.2 GB of tables) in flight and re-read every row from HBM.
 int pick_qpc(int B, int Nd, bool phase2_only, int Co = 0, size_t table_bytes = 0) {
     int qpc = QT;
-    const int floor_q = phase2_only ? 8 : 16;
+    int floor_q = phase2_only ? 8 : 16;
+    if (phase2_only && Co > 0) {
+        const int lpp = std::max(1, std::min(Co / 4, 32));   // lanes per point in phase 2
+        floor_q = std::max(8, 8 * (32 / lpp));                // one pass of the CTA's 8 warps
+    }
     while (qpc > floor_q && (long long)B * ((Nd + qpc - 1) / qpc) < 4 * 148) qpc >>= 1;
     if (phase2_only && table_bytes > 0) {
-        const int lpp = std::max(1, std::min(Co / 4, 32));   // lanes per point in phase 2
-        const int min_q = std::max(8, 8 * (32 / lpp));        // one pass of the CTA's 8 warps
         const long long slots = 148LL * LS_P2_CTAS, budget = 64LL << 20;
-        while (qpc > min_q) {
+        while (qpc > floor_q) {
             const long long per_inst = (Nd + qpc - 1) / qpc;
             const long long in_flight = (slots + per_inst - 1) / per_inst;
             if (in_flight * (long long)table_bytes <= budget) break;
@@ -408,10 +430,13 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         if (fa.n_levels > 0) {
             if (sc) {  // FPS only needs xyz: it runs beside layers 0..first down-sampling layer
                 LS_CHECK_CUDA(cudaEventRecord(sc->fork_ev, st));
-                LS_CHECK_CUDA(cudaStreamWaitEvent(sc->s, sc->fork_ev, 0));
-                rc = launch_fps(fa, B, sc->s);
-                if (rc != LS_OK) return rc;
-                LS_CHECK_CUDA(cudaEventRecord(sc->join_fps, sc->s));
+                LS_CHECK_CUDA(cudaStreamWaitEvent(sc->s_fps, sc->fork_ev, 0));
+                rc = launch_fps(fa, B, sc->s_fps);
+                if (rc != LS_OK) {
+                    cudaStreamWaitEvent(st, sc->fork_ev, 0);
+                    return rc;
+                }
+                LS_CHECK_CUDA(cudaEventRecord(sc->join_fps, sc->s_fps));
                 fps_pending = true;
             } else {
                 ProfScope ps(1, -1, st);
@@ -456,60 +481,16 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         ea.idx_out = io->knn_idx[i];
         ea.idx_in = io->force_knn_idx[i];
 
-        // ---- point-level GEMM tables (layers >= 1): independent of the graph, so they run on the side stream
-        //      while the kNN chain below occupies the main stream
-        bool tables_forked = false;
-        if (i > 0) {
-            const int nb = L.attention ? 2 : 1;
-            const int r_src = 2 * nb * Co, r_dst = (2 * nb + (L.attention ? 2 : 0)) * Co;
-            cudaStream_t ts = st;
-            if (sc && ea.idx_in == nullptr) {
-                LS_CHECK_CUDA(cudaEventRecord(sc->fork_ev, st));
-                LS_CHECK_CUDA(cudaStreamWaitEvent(sc->s, sc->fork_ev, 0));
-                ts = sc->s;
-                tables_forked = true;
-            }
-            {
-                ProfScope pg(3, i, ts);
-                GemmArgs g{};
-                g.K = Ci;
-                g.ldw = Ci;
-                g.B = B;
-                g.point_major = 1;
-                g.c_out = Co;
-                // source table
-                g.W = L.w_src;
-                g.Wtc = L.w_src_tc;
-                g.R = r_src;
-                g.X = src_f;
-                g.n_per_b = 3 * Ns;
-                g.npts = Ns;
-                g.x_sb = (long long)Ci * 3 * Ns;
-                g.x_sk = 3LL * Ns;
-                g.out = p.psrc;
-                rc = launch_gemm(g, ts);
-                if (rc != LS_OK) return rc;
-                // dst table
-                g.W = L.w_dst;
-                g.Wtc = L.w_dst_tc;
-                g.R = r_dst;
-                g.X = dst_f;
-                g.n_per_b = 3 * Nd;
-                g.npts = Nd;
-                g.x_sb = (long long)Ci * 3 * Nd;
-                g.x_sk = 3LL * Nd;
-                g.out = p.pdst;
-                rc = launch_gemm(g, ts);
-                if (rc != LS_OK) return rc;
-            }
-            if (tables_forked) LS_CHECK_CUDA(cudaEventRecord(sc->join_tab, sc->s));
-            ea.psrc = p.psrc;
-            ea.pdst = p.pdst;
-            ea.row_s = r_src * 3;
-            ea.row_d = r_dst * 3;
+        // the point-level table GEMMs (layers >= 1) only need the layer input: they may start now on the side stream
+        const int nb = L.attention ? 2 : 1;
+        const int r_src = 2 * nb * Co, r_dst = (2 * nb + (L.attention ? 2 : 0)) * Co;
+        const bool side_tables = i > 0 && sc != nullptr;
+        if (side_tables) {
+            LS_CHECK_CUDA(cudaEventRecord(sc->fork_ev, st));
+            LS_CHECK_CUDA(cudaStreamWaitEvent(sc->s_tab, sc->fork_ev, 0));
         }
 
-        // ---- kNN graph
+        // ---- kNN graph (whole batch, caller's stream)
         if (ea.idx_in == nullptr && Ns <= SMALL_NS && !(g_use_knn_tc && Ns >= small_tc_min())) {
             ProfScope ps(4, i, st);
             dim3 gs((Nd + 7) / 8, B);
@@ -566,14 +547,85 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ea.idx_in = p.kidx;
             ea.idx_out = nullptr;
         }
-        ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr, Co,
-                          i > 0 ? sizeof(float) * ((size_t)ea.row_s * Ns + (size_t)ea.row_d * Nd) : 0);
-        if (tables_forked) LS_CHECK_CUDA(cudaStreamWaitEvent(st, sc->join_tab, 0));
-        {
+
+        if (i == 0) {
+            ea.qpc = pick_qpc(B, Nd, ea.idx_in != nullptr);
+            ea.w0 = L.w0;
             ProfScope ps(4, i, st);
-            if (i == 0) ea.w0 = L.w0;
-            rc = launch_edge(i == 0 ? MODE_L0 : (L.attention ? MODE_ATT : MODE_MEAN), ea, st);
+            rc = launch_edge(MODE_L0, ea, st);
             if (rc != LS_OK) return rc;
+        } else {
+            // ---- waves of {table GEMMs (side stream) -> EdgeConv + pooling (caller's stream)}
+            const size_t tab_s = (size_t)r_src * 3 * Ns, tab_d = (size_t)r_dst * 3 * Nd;  // floats per instance
+            const size_t tab_bytes = sizeof(float) * (tab_s + tab_d);
+            int W = B;
+            if (g_wave_bytes > 0) W = (int)std::max<long long>(1, std::min<long long>(B, g_wave_bytes / (long long)tab_bytes));
+            if (W * 2 > B) W = B;  // fewer than two full waves: not worth splitting
+            const int n_waves = (B + W - 1) / W;
+            cudaStream_t ts = side_tables ? sc->s_tab : st;
+            const EdgeArgs ea0 = ea;
+            for (int wv = 0; wv < n_waves; ++wv) {
+                const int b0 = wv * W, Bw = std::min(W, B - b0), slot = n_waves > 1 ? (wv & 1) : 0;
+                float* psrc_w = p.psrc + (size_t)slot * W * tab_s;
+                float* pdst_w = p.pdst + (size_t)slot * W * tab_d;
+                if (side_tables && wv >= 2) LS_CHECK_CUDA(cudaStreamWaitEvent(ts, sc->ev_edge[slot], 0));  // slot drained
+                {
+                    ProfScope pg(3, i, ts);
+                    GemmArgs g{};
+                    g.K = Ci;
+                    g.ldw = Ci;
+                    g.B = Bw;
+                    g.point_major = 1;
+                    g.c_out = Co;
+                    // source table
+                    g.W = L.w_src;
+                    g.Wtc = L.w_src_tc;
+                    g.R = r_src;
+                    g.X = src_f + (size_t)b0 * Ci * 3 * Ns;
+                    g.n_per_b = 3 * Ns;
+                    g.npts = Ns;
+                    g.x_sb = (long long)Ci * 3 * Ns;
+                    g.x_sk = 3LL * Ns;
+                    g.out = psrc_w;
+                    rc = launch_gemm(g, ts);
+                    if (rc == LS_OK) {
+                        // dst table
+                        g.W = L.w_dst;
+                        g.Wtc = L.w_dst_tc;
+                        g.R = r_dst;
+                        g.X = dst_f + (size_t)b0 * Ci * 3 * Nd;
+                        g.n_per_b = 3 * Nd;
+                        g.npts = Nd;
+                        g.x_sb = (long long)Ci * 3 * Nd;
+                        g.x_sk = 3LL * Nd;
+                        g.out = pdst_w;
+                        rc = launch_gemm(g, ts);
+                    }
+                }
+                if (side_tables) {  // join the side stream (also on the error path: an un-joined fork would break a capture)
+                    cudaEventRecord(sc->ev_tab[slot], ts);
+                    cudaStreamWaitEvent(st, sc->ev_tab[slot], 0);
+                }
+                if (rc != LS_OK) return rc;
+                ea = ea0;
+                ea.B = Bw;
+                ea.src_f = ea0.src_f + (size_t)b0 * Ci * 3 * Ns;
+                ea.dst_f = ea0.dst_f + (size_t)b0 * Ci * 3 * Nd;
+                ea.out = ea0.out + (size_t)b0 * Co * 3 * Nd;
+                if (ea0.idx_in) ea.idx_in = ea0.idx_in + (size_t)b0 * Nd * LS_KNN_K;
+                if (ea0.idx_out) ea.idx_out = ea0.idx_out + (size_t)b0 * Nd * LS_KNN_K;
+                ea.psrc = psrc_w;
+                ea.pdst = pdst_w;
+                ea.row_s = r_src * 3;
+                ea.row_d = r_dst * 3;
+                ea.qpc = pick_qpc(Bw, Nd, ea.idx_in != nullptr, Co, n_waves > 1 ? 0 : tab_bytes);  // a wave's tables fit L2 by construction
+                {
+                    ProfScope ps(4, i, st);
+                    rc = launch_edge(L.attention ? MODE_ATT : MODE_MEAN, ea, st);
+                    if (rc != LS_OK) return rc;
+                }
+                if (side_tables && wv + 2 < n_waves) LS_CHECK_CUDA(cudaEventRecord(sc->ev_edge[slot], st));
+            }
         }
         if (L.global_conv) {
             ProfScope ps(5, i, st);
@@ -683,6 +735,16 @@ int ls_set_overlap(int32_t on) {
 }
 int ls_set_tensor_cores(int32_t on) {
     ls::g_use_tensor_cores = on != 0;
+    return LS_OK;
+}
+int ls_set_wave_bytes(int64_t bytes) {
+    LS_REQUIRE(bytes >= 0, "wave bytes must be >= 0");
+    ls::g_wave_bytes = bytes;
+    return LS_OK;
+}
+int ls_set_gemm_variant(int32_t variant) {
+    LS_REQUIRE(variant == 1 || variant == 2, "gemm variant must be 1 (per-tile CTAs) or 2 (persistent, warp-specialised)");
+    ls::g_gemm_variant = variant;
     return LS_OK;
 }
 int ls_vn_linear(const float* W, const float* packed, const float* X, float* out, int32_t R, int32_t K, int32_t ldw,

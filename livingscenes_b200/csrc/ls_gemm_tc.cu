@@ -17,6 +17,22 @@
 //   * epilogue: each warp tcgen05.ld's its 32 TMEM lanes (= 32 weight rows) and stores either the
 //     point-major gather table (128 B coalesced across lanes) or the channel-major tensor (+bias, relu).
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+//
+// Two kernels share the operand images and descriptors:
+//   k_gemm_tc   (round 1) one CTA per tile, operands staged through registers, 2-stage ring, __syncthreads per
+//               k-block.  Kept as the A/B reference (ls_set_gemm_variant(1)).
+//   k_gemm_tc2  (default) persistent, warp-specialised: grid = #SMs, every CTA loops over output tiles;
+//               warp 8     producer: cp.async.bulk (TMA bulk, mbarrier complete_tx) of the 16 KB weight image of
+//                          the k-block and of the raw fp32 activation rows (512 B per k row and tile);
+//               warps 4-7  transform: raw [16 k][128 n] tile -> hi/lo TF32 split in the canonical K-major UMMA
+//                          image (the 4x4 register transpose of round 1, now smem -> smem);
+//               warp 9     one thread issues the tcgen05.mma's; tcgen05.commit frees the operand stage / publishes
+//                          the accumulator;
+//               warps 0-3  epilogue: tcgen05.ld of accumulator buffer i while the MMAs of tile i+1 fill buffer
+//                          i^1 (2 x 128 TMEM columns).
+//               Rings: 3 operand stages (32 KB each), 4 raw stages (8 KB each); no __syncthreads in the tile loop.
+#include <atomic>
+
 #include "ls_common.cuh"
 
 namespace ls {
@@ -289,6 +305,285 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
     }
 }
 
+
+// =====================================================================================================
+// k_gemm_tc2: persistent warp-specialised variant (see the header comment)
+// =====================================================================================================
+constexpr int G2_S = 3, G2_RS = 4;                 // operand stages, raw activation stages
+constexpr int G2_THREADS = 320;                     // warps 0-3 epilogue, 4-7 transform, 8 producer, 9 MMA
+constexpr int G2_XF_WARP0 = 4, G2_PROD_WARP = 8, G2_MMA_WARP = 9;
+constexpr int G2_TMEM_COLS = 2 * TN;                // two accumulator buffers
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct G2Shared {
+    float a[G2_S][2][A_STAGE_FLOATS];  // [stage][hi/lo] weight images (bulk copies)
+    float b[G2_S][2][B_STAGE_FLOATS];  // [stage][hi/lo] activation images (written by the transform warps)
+    float raw[G2_RS][TKB][TN];         // raw fp32 activation rows (bulk copies)
+    float epi[4][32 * 33];             // per epilogue warp: 32 x 32 transpose tile for channel-major stores
+    long long col_base[TN];            // output offset of every tile column (-1 = out of range)
+    long long col_bias[TN];
+    uint64_t full_a[G2_S], full_b[G2_S], empty[G2_S], raw_full[G2_RS], raw_empty[G2_RS], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <bool PM>
+__global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, const float* __restrict__ wpk, int n_kb, int n_mt,
+                                                            int n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    G2Shared& sh = *reinterpret_cast<G2Shared*>(smem_raw);
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const long long ncols = (long long)a.B * a.n_per_b;
+
+    if (t == 0) {
+        for (int s = 0; s < G2_S; ++s) {
+            mbar_init(&sh.full_a[s], 1);
+            mbar_init(&sh.full_b[s], 128);
+            mbar_init(&sh.empty[s], 1);
+        }
+        for (int r = 0; r < G2_RS; ++r) {
+            mbar_init(&sh.raw_full[r], 1);
+            mbar_init(&sh.raw_empty[r], 128);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sh.tmem_full[i], 1);
+            mbar_init(&sh.tmem_empty[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == G2_MMA_WARP) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+                     "r"(G2_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = sh.tmem_base;
+
+    if (w == G2_PROD_WARP) {
+        // ================================================================ producer: bulk copies
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile % n_mt;
+            const long long c0 = (long long)(tile / n_mt) * TN;
+            const long long c_end = (c0 + TN < ncols) ? c0 + TN : ncols;
+            const float* wtile = wpk + (size_t)mt * n_kb * (2 * A_STAGE_FLOATS);
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                // raw activation rows of this k-block: row k of the tile is contiguous per instance
+                const int r = it % G2_RS;
+                if (it >= G2_RS) mbar_wait(&sh.raw_empty[r], ((it / G2_RS) - 1) & 1);
+                const int k_rows = (a.K - kb * TKB) < TKB ? (a.K - kb * TKB) : TKB;
+                if (lane == 0) mbar_arrive_expect_tx(&sh.raw_full[r], (uint32_t)((long long)k_rows * (c_end - c0) * 4));
+                __syncwarp();
+                if (lane < k_rows) {
+                    const long long k = (long long)kb * TKB + lane;
+                    long long j = c0;
+                    while (j < c_end) {
+                        const long long bb = j / a.n_per_b, n = j - bb * a.n_per_b;
+                        long long len = (long long)a.n_per_b - n;
+                        if (len > c_end - j) len = c_end - j;
+                        bulk_g2s(&sh.raw[r][lane][j - c0], a.X + bb * a.x_sb + k * a.x_sk + n, (uint32_t)(len * 4),
+                                 &sh.raw_full[r]);
+                        j += len;
+                    }
+                }
+                // weight image of (m-tile, k-block): one contiguous 16 KB block (hi then lo)
+                const int s = it % G2_S;
+                if (it >= G2_S) mbar_wait(&sh.empty[s], ((it / G2_S) - 1) & 1);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&sh.full_a[s], 2 * A_STAGE_FLOATS * 4);
+                    bulk_g2s(&sh.a[s][0][0], wtile + (size_t)kb * (2 * A_STAGE_FLOATS), 2 * A_STAGE_FLOATS * 4, &sh.full_a[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (w == G2_MMA_WARP) {
+        // ================================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                if (lt >= 2) {  // the epilogue must have drained this accumulator buffer
+                    mbar_wait(&sh.tmem_empty[acc], ((lt >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint32_t d = tmem + (uint32_t)(acc * TN);
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    const int s = it % G2_S;
+                    mbar_wait(&sh.full_a[s], (it / G2_S) & 1);
+                    mbar_wait(&sh.full_b[s], (it / G2_S) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(&sh.a[s][0][0]), a_lo = smem_u32(&sh.a[s][1][0]);
+                    const uint32_t b_hi = smem_u32(&sh.b[s][0][0]), b_lo = smem_u32(&sh.b[s][1][0]);
+#pragma unroll
+                    for (int ss = 0; ss < TKB / 8; ++ss) {
+                        const uint64_t dah = make_desc(a_hi + ss * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                        const uint64_t dal = make_desc(a_lo + ss * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
+                        const uint64_t dbh = make_desc(b_hi + ss * 2 * (TN / 8) * 128, (TN / 8) * 128, 128);
+                        const uint64_t dbl = make_desc(b_lo + ss * 2 * (TN / 8) * 128, (TN / 8) * 128, 128);
+                        umma_tf32(d, dal, dbh, (kb | ss) != 0);
+                        umma_tf32(d, dah, dbl, 1);
+                        umma_tf32(d, dah, dbh, 1);
+                    }
+                    umma_commit(&sh.empty[s]);  // frees the operand stage when the MMAs have read it
+                    if (kb == n_kb - 1) umma_commit(&sh.tmem_full[acc]);
+                }
+            }
+        }
+    } else if (w >= G2_XF_WARP0) {
+        // ================================================================ transform: raw fp32 -> hi/lo K-major images
+        const int kc = w - G2_XF_WARP0;  // k-core (4 k rows) owned by this warp
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long c0 = (long long)(tile / n_mt) * TN;
+            const bool col_ok = c0 + lane * 4 < ncols;  // ncols % 4 == 0: a 4-column group is all in or all out
+            for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                const int r = it % G2_RS;
+                mbar_wait(&sh.raw_full[r], (it / G2_RS) & 1);
+                float4 v[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int kl = kc * 4 + rr;
+                    v[rr] = (col_ok && kb * TKB + kl < a.K) ? *reinterpret_cast<const float4*>(&sh.raw[r][kl][lane * 4])
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                const int s = it % G2_S;
+                if (it >= G2_S) mbar_wait(&sh.empty[s], ((it / G2_S) - 1) & 1);
+                // the 4(k) x 4(n) block transposed: four 16-byte core-matrix rows of [kcore][ngroup][8 n][4 k],
+                // stored in a lane-rotated order (each quarter-warp hits 8 distinct 16-byte bank groups)
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int i = (s4 + (lane >> 1)) & 3;
+                    float4 c;
+                    c.x = i == 0 ? v[0].x : (i == 1 ? v[0].y : (i == 2 ? v[0].z : v[0].w));
+                    c.y = i == 0 ? v[1].x : (i == 1 ? v[1].y : (i == 2 ? v[1].z : v[1].w));
+                    c.z = i == 0 ? v[2].x : (i == 1 ? v[2].y : (i == 2 ? v[2].z : v[2].w));
+                    c.w = i == 0 ? v[3].x : (i == 1 ? v[3].y : (i == 2 ? v[3].z : v[3].w));
+                    float4 hi, lo;
+                    hi.x = __uint_as_float((__float_as_uint(c.x) + 0x1000u) & 0xffffe000u);
+                    hi.y = __uint_as_float((__float_as_uint(c.y) + 0x1000u) & 0xffffe000u);
+                    hi.z = __uint_as_float((__float_as_uint(c.z) + 0x1000u) & 0xffffe000u);
+                    hi.w = __uint_as_float((__float_as_uint(c.w) + 0x1000u) & 0xffffe000u);
+                    lo.x = c.x - hi.x;
+                    lo.y = c.y - hi.y;
+                    lo.z = c.z - hi.z;
+                    lo.w = c.w - hi.w;
+                    const int n = lane * 4 + i;
+                    const int off = ((kc * (TN / 8) + (n >> 3)) * 8 + (n & 7)) * 4;
+                    *reinterpret_cast<float4*>(&sh.b[s][0][off]) = hi;
+                    *reinterpret_cast<float4*>(&sh.b[s][1][off]) = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(&sh.full_b[s]);
+                mbar_arrive(&sh.raw_empty[r]);
+            }
+        }
+    } else {
+        // ================================================================ epilogue: TMEM -> registers -> global
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int acc = lt & 1, mt = tile % n_mt;
+            const long long c0 = (long long)(tile / n_mt) * TN;
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // the previous tile's column tables are no longer read
+            {
+                const long long j = c0 + t;
+                long long base = -1, boff = 0;
+                if (j < ncols) {
+                    const long long b = j / a.n_per_b;
+                    const int n = (int)(j - b * a.n_per_b);
+                    const int axis = a.npts > 0 ? n / a.npts : 0;
+                    if (PM) {
+                        const int pt = n - axis * a.npts;
+                        base = (b * a.npts + pt) * ((long long)a.R * 3) + (long long)axis * a.c_out;
+                    } else {
+                        base = b * a.o_sb + n;
+                        boff = b * a.bias_sb + (a.bias_axis ? axis : 0);
+                    }
+                }
+                sh.col_base[t] = base;
+                sh.col_bias[t] = boff;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&sh.tmem_full[acc], (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int r0 = mt * TM;
+            const int r = r0 + w * 32 + lane;  // TMEM lane == tile row
+            const bool row_ok = r < a.R;
+            long long row_off = 0;
+            if (PM) {
+                const int part = row_ok ? r / a.c_out : 0;
+                row_off = (long long)part * 3 * a.c_out + (r - part * a.c_out);
+            }
+#pragma unroll 1
+            for (int cc = 0; cc < TN; cc += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * TN + cc);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == TN - 32) {  // this thread's last read of the buffer: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&sh.tmem_empty[acc]);
+                }
+                if (PM) {
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const long long base = sh.col_base[cc + j];
+                            if (base >= 0) a.out[base + row_off] = __uint_as_float(v[j]);  // lanes = consecutive channels
+                        }
+                    }
+                } else {
+                    // channel-major: transpose the warp's 32 rows x 32 columns so that lanes store consecutive columns
+                    float* tl = &sh.epi[w][0];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tl[lane * 33 + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    const long long base = sh.col_base[cc + lane];
+                    const long long bo = sh.col_bias[cc + lane];
+                    if (base >= 0) {
+#pragma unroll 8
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const int row = r0 + w * 32 + rr;
+                            if (row >= a.R) break;
+                            float val = tl[rr * 33 + lane];
+                            if (a.bias) val += __ldg(a.bias + bo + (long long)row * a.bias_sr);
+                            if (a.relu) val = fmaxf(val, 0.f);
+                            a.out[base + (long long)row * a.o_sr] = val;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == G2_MMA_WARP) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(G2_TMEM_COLS) : "memory");
+    }
+}
+
 // W [R][ldw] row-major -> per (m-tile, k-block): hi image then lo image, each [kcore 4][mgroup 16][8 rows][4 k]
 __global__ void k_tc_pack_weights(const float* __restrict__ W, int R, int K, int ldw, float* __restrict__ out, int n_kb) {
     const int mt = blockIdx.y, kb = blockIdx.x;
@@ -330,6 +625,20 @@ bool gemm_tc_supported(const GemmArgs& a) {
     return true;
 }
 
+int g_gemm_variant = 2;  // 2: persistent warp-specialised k_gemm_tc2; 1: round-1 k_gemm_tc
+
+static int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
     LS_REQUIRE(packed != nullptr, "gemm_tc: packed weights missing");
     LS_REQUIRE(gemm_tc_supported(a), "gemm_tc: unsupported activation geometry");
@@ -339,19 +648,35 @@ int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
                    "gemm_tc: bad point-major geometry");
     const long long ncols = (long long)a.B * a.n_per_b;
     const int n_kb = (a.K + TKB - 1) / TKB;
-    dim3 grid((unsigned)((ncols + TN - 1) / TN), (unsigned)((a.R + TM - 1) / TM));
-    const size_t smem = sizeof(TcShared) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    // the dynamic shared-memory opt-in is per device: set it on every launch (cheap, legal under stream capture)
+    // instead of caching a process-wide flag that a second device in the same process would never see
+    if (g_gemm_variant == 1) {
+        dim3 grid((unsigned)((ncols + TN - 1) / TN), (unsigned)((a.R + TM - 1) / TM));
+        const size_t smem = sizeof(TcShared) + 128;
+        if (a.point_major) {
+            LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_gemm_tc<true><<<grid, TC_THREADS, smem, st>>>(a, packed, n_kb);
+        } else {
+            LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_gemm_tc<false><<<grid, TC_THREADS, smem, st>>>(a, packed, n_kb);
+        }
+        LS_CHECK_LAUNCH("k_gemm_tc");
+        return LS_OK;
     }
-    if (a.point_major)
-        k_gemm_tc<true><<<grid, TC_THREADS, smem, st>>>(a, packed, n_kb);
-    else
-        k_gemm_tc<false><<<grid, TC_THREADS, smem, st>>>(a, packed, n_kb);
-    LS_CHECK_LAUNCH("k_gemm_tc");
+    const long long n_ct = (ncols + TN - 1) / TN;
+    const int n_mt = (a.R + TM - 1) / TM;
+    LS_REQUIRE(n_ct * n_mt < (1LL << 31), "gemm_tc: too many tiles");
+    const int n_tiles = (int)(n_ct * n_mt);
+    const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
+    const size_t smem = sizeof(G2Shared) + 128;
+    if (a.point_major) {
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gemm_tc2<true><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles);
+    } else {
+        LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gemm_tc2<false><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles);
+    }
+    LS_CHECK_LAUNCH("k_gemm_tc2");
     return LS_OK;
 }
 

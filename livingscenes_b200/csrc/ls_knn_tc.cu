@@ -446,11 +446,9 @@ int launch_knn_tc(const KnnTcArgs& a, int B, cudaStream_t st) {
     LS_REQUIRE(a.img_s && a.img_q && a.nrm_s && a.nrm_q && a.cand && a.cand_dt && a.cnt && a.e2, "knn_tc: null pointer");
     LS_REQUIRE(a.Ns >= LS_KNN_K && a.Ns <= 65535 && a.Nd >= 1, "knn_tc: need 16 <= Ns <= 65535");
     const size_t smem = sizeof(KtShared) + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
-        LS_CHECK_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // the opt-in is per device and per process: set it on every launch (a few hundred ns; legal during stream
+    // capture) instead of caching a process-wide flag that a second device would never see
+    LS_CHECK_CUDA(cudaFuncSetAttribute(k_knn_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_knn_tc<<<dim3(a.n_pt_q, B), KT_THREADS, smem, st>>>(a);
     LS_CHECK_LAUNCH("k_knn_tc");
     return LS_OK;

@@ -1,7 +1,9 @@
 """Seeded synthetic inputs and stand-in weights (no reference counterpart): the workload generators of bench.py,
 scripts/ and the tests.  Pure torch on the CPU; nothing here computes any part of the hot path.
 
-  synth_instances    SURVEY.md 8d synthetic clouds (noisy ellipsoidal shells)
+  synth_instances    SURVEY.md 8d synthetic clouds (noisy ellipsoidal shells; the round-1 fixtures use these)
+  synth_parts        asymmetric composite objects (random boxes of one "furniture-like" assembly): every instance has
+                     a unique pose and a distinctive shape, so a planted permutation / SE(3) is recoverable
   random_rotations   uniform random proper rotations
   random_state_dict  seeded weights with the shipped checkpoint's keys and shapes
 """
@@ -91,6 +93,47 @@ def synth_instances(B: int, N: int, seed: int) -> torch.Tensor:
     return p.transpose(1, 2).contiguous().float()
 
 
+def synth_parts(B: int, N: int, seed: int, noise: float = 0.002) -> torch.Tensor:
+    """Asymmetric composite objects, [B,3,N] fp32.  An instance is the surface of 4-7 axis-aligned boxes of random
+    size hung on a random "seat" slab (legs of different length/offset, a back, an arm on ONE side), scaled by
+    U(0.5, 1.5) and translated by U(-2, 2)^3.  Unlike the ellipsoidal shells of ``synth_instances`` the shapes have no
+    rotational symmetry, so the equivariant code pins the rotation and the invariant code separates the instances
+    (bench.py / scripts/run_configs.py plant a permutation + SE(3) and check that the path recovers them)."""
+    g = torch.Generator().manual_seed(seed)
+    out = torch.empty(B, N, 3)
+    for b in range(B):
+        n_box = int(torch.randint(4, 8, (1,), generator=g))
+        u = lambda *s: torch.rand(*s, generator=g)
+        seat = torch.tensor([0.35, 0.30, 0.04]) * (0.7 + 0.6 * u(3))
+        half = [seat]
+        cen = [torch.zeros(3)]
+        for k in range(n_box - 1):
+            kind = k % 3
+            if kind == 0:    # a leg below the seat, its own length and footprint position
+                h = torch.tensor([0.03, 0.03, 0.10 + 0.25 * float(u(1))]) * (0.7 + 0.6 * u(3))
+                c = torch.stack([(u(1)[0] * 2 - 1) * seat[0] * 0.9, (u(1)[0] * 2 - 1) * seat[1] * 0.9, -seat[2] - h[2]])
+            elif kind == 1:  # a back / panel above one edge
+                h = torch.tensor([0.30, 0.03, 0.15 + 0.25 * float(u(1))]) * (0.6 + 0.8 * u(3))
+                c = torch.stack([(u(1)[0] * 2 - 1) * 0.1, seat[1] * (0.6 + 0.4 * u(1)[0]), seat[2] + h[2]])
+            else:            # an arm / shelf on the +x side only
+                h = torch.tensor([0.04, 0.20, 0.05]) * (0.6 + 0.8 * u(3))
+                c = torch.stack([seat[0] * (0.7 + 0.3 * u(1)[0]), (u(1)[0] * 2 - 1) * 0.1, seat[2] + 0.05 + 0.2 * u(1)[0]])
+            half.append(h)
+            cen.append(c)
+        half, cen = torch.stack(half), torch.stack(cen)
+        # area-weighted surface sampling: pick a box, then one of its 6 faces
+        fa = torch.stack([half[:, 1] * half[:, 2], half[:, 0] * half[:, 2], half[:, 0] * half[:, 1]], 1)  # face areas /4
+        w = fa.repeat(1, 2).reshape(-1)
+        pick = torch.multinomial(w / w.sum(), N, replacement=True, generator=g)
+        bi, fi = pick // 6, pick % 6
+        p = (u(N, 3) * 2 - 1) * half[bi]
+        ax, sgn = fi % 3, (fi // 3).float() * 2 - 1
+        p[torch.arange(N), ax] = sgn * half[bi, ax]
+        p = (p + cen[bi]) * (0.5 + float(u(1)))
+        out[b] = p + noise * torch.randn(N, 3, generator=g) + (u(1, 3) * 4 - 2)
+    return out.transpose(1, 2).contiguous().float()
+
+
 def random_rotations(B: int, seed: int) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(B, 3, 3, generator=g, dtype=torch.float64)
@@ -98,3 +141,28 @@ def random_rotations(B: int, seed: int) -> torch.Tensor:
     Q = Q * torch.sign(torch.diagonal(R, dim1=1, dim2=2))[:, None, :]
     Q[:, :, 0] *= torch.det(Q)[:, None]
     return Q.float()
+
+
+def lcg_uniform(n: int, seed: int) -> torch.Tensor:
+    """n doubles in [0,1) from a 64-bit LCG evaluated in closed form per index with numpy uint64 arithmetic
+    (Knuth MMIX multiplier, splitmix-style finaliser): bit-reproducible on every platform / torch version, so
+    large query sets (config C5: 4 x 100 000 points) are regenerated from the seed instead of stored."""
+    import numpy as np
+
+    with np.errstate(over="ignore"):
+        i = np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+        z = i * np.uint64(6364136223846793005) + np.uint64(1442695040888963407)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return torch.from_numpy((z >> np.uint64(11)).astype(np.float64) / float(1 << 53))
+
+
+def sdf_queries(code_s: torch.Tensor, code_t: torch.Tensor, M: int, seed: int) -> torch.Tensor:
+    """Config C5 queries: M points per instance, uniform in the 1.1-padded unit cube of the instance's canonical
+    frame (mesh_extractor2.py:100) mapped to the world by q*s + t.  code_s [B], code_t [B,1,3] -> [B,M,3] fp32."""
+    B = code_s.shape[0]
+    u = lcg_uniform(B * M * 3, seed).reshape(B, M, 3).float()
+    return ((u - 0.5) * 1.1) * code_s.reshape(B, 1, 1).cpu() + code_t.reshape(B, 1, 3).cpu()

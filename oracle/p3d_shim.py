@@ -43,6 +43,12 @@ import types
 import torch
 
 EXACT = True  # parity mode; bench's CPU-timing leg flips this to False
+# eager-GPU timing leg of bench.py ("the reference's eager PyTorch path on the same B200"): the ops run on the
+# tensors' device.  kNN = fp32 matmul form + topk (cheapest honest torch form); FPS_IMPL, when set, is a callable
+# (points[B,P,3], K) -> (pts, idx) standing in for pytorch3d's CUDA FPS kernel (a python loop of ~8 torch ops per
+# selected point would misrepresent it).
+ON_DEVICE = False
+FPS_IMPL = None
 
 
 def _sqdist_f64(q: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
@@ -66,6 +72,14 @@ def knn_points(p1, p2, lengths1=None, lengths2=None, norm: int = 2, K: int = 1,
     P2 = p2.shape[1]
     assert K <= P2, "oracle shim: K must not exceed the number of source points"
     dev = p1.device
+    if ON_DEVICE:
+        a, s_ = p1.detach(), p2.detach()
+        d = (a * a).sum(-1)[:, :, None] + (s_ * s_).sum(-1)[:, None, :] - 2.0 * torch.bmm(a, s_.transpose(1, 2))
+        dv, di = torch.topk(d, K, dim=-1, largest=False, sorted=True)
+        nn_ = None
+        if return_nn:
+            nn_ = torch.gather(s_[:, None].expand(B, P1, P2, D), 2, di[..., None].expand(B, P1, K, D))
+        return dv.clamp_min(0), di, nn_
     p1c, p2c = p1.detach().cpu(), p2.detach().cpu()
     idx = torch.empty(B, P1, K, dtype=torch.int64)
     dists = torch.empty(B, P1, K, dtype=p1.dtype)
@@ -98,6 +112,8 @@ def sample_farthest_points(points, lengths=None, K: int = 50, random_start_point
     assert points.dim() == 3 and points.shape[2] == 3
     B, P, _ = points.shape
     assert K <= P
+    if ON_DEVICE and FPS_IMPL is not None and start_idx is None:
+        return FPS_IMPL(points, K)
     x = points.detach().cpu().float()
     px, py, pz = x[..., 0].contiguous(), x[..., 1].contiguous(), x[..., 2].contiguous()
     idx = torch.zeros(B, K, dtype=torch.int64)

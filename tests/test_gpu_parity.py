@@ -368,6 +368,60 @@ def test_vn_linear_fp32_accurate(tensor_cores, B, Ci, Co, N, dev):
     assert err < (1e-5 if tensor_cores else 2e-6), f"max-rel error {err:.2e}"
 
 
+@pytest.mark.parametrize("B,Ci,Co,N", [(3, 32, 64, 1024), (37, 64, 384, 512), (300, 128, 768, 128), (7, 256, 2048, 32),
+                                       (2, 512, 257, 32), (1, 257, 768, 1000), (4, 96, 40, 36), (256, 32, 128, 1024)])
+def test_gemm_persistent_equals_per_tile_kernel(B, Ci, Co, N, dev):
+    """The persistent warp-specialised tcgen05 GEMM (bulk-TMA fed, double-buffered TMEM; many tiles per CTA at the
+    larger sizes) issues the same MMAs in the same order as the round-1 one-tile-per-CTA kernel: bit-identical."""
+    import livingscenes_b200 as ls
+    from livingscenes_b200 import _lib
+
+    g = torch.Generator().manual_seed(B * 1000 + Ci)
+    W = ((torch.rand(Co, Ci, generator=g) * 2 - 1) / Ci ** 0.5).to(dev)
+    v = torch.randn(B, Ci, 3, N, generator=g).to(dev)
+    try:
+        _lib.set_gemm_variant(1)
+        a = ls.vn_linear(W, v, tensor_cores=True)
+        _lib.set_gemm_variant(2)
+        b = ls.vn_linear(W, v, tensor_cores=True)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_gemm_variant(2)
+    assert torch.equal(a, b)
+    ref = torch.einsum("oc,bcan->boan", W.double().cpu(), v.double().cpu())
+    assert float((b.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_encoder_wave_schedule_invariance(dev, oracle_R):
+    """The {table GEMM -> EdgeConv} wave schedule (L2-resident gather tables, two alternating slots, side stream)
+    does not change a single bit: whole-batch launches, tiny waves, GEMM variant 1, with and without overlap."""
+    from livingscenes_b200 import _lib
+
+    enc = _model("random", dev).encoder
+    x = oracle_R.synth_instances(23, 1024, 777).to(dev)
+    try:
+        _lib.set_wave_bytes(0)
+        ref = enc.run(x, normalize=True, taps=True)
+        torch.cuda.synchronize()
+        for wave_mb, overlap, variant in ((28, True, 2), (6, True, 2), (6, False, 2), (12, True, 1), (1, True, 2)):
+            _lib.set_wave_bytes(wave_mb << 20)
+            _lib.set_overlap(overlap)
+            _lib.set_gemm_variant(variant)
+            for _ in range(2):
+                r = enc.run(x, normalize=True, taps=True)
+            torch.cuda.synchronize()
+            for i, (ia, ib) in enumerate(zip(ref["knn_idx"], r["knn_idx"])):
+                assert torch.equal(ia, ib), f"layer {i} wave_mb={wave_mb}"
+            for i, (fa, fb) in enumerate(zip(ref["feat"], r["feat"])):
+                assert torch.equal(fa, fb), f"features of layer {i} wave_mb={wave_mb} overlap={overlap} variant={variant}"
+            for k in ("z_so3", "z_inv", "scale", "center"):
+                assert torch.equal(ref[k], r[k]), k
+    finally:
+        _lib.set_wave_bytes(28 << 20)
+        _lib.set_overlap(True)
+        _lib.set_gemm_variant(2)
+
+
 # ------------------------------------------------------------------------------------------ encoder
 @pytest.mark.parametrize("tag", ["random", "shipped"])
 def test_encoder_teacher_forced_matches_golden(tag, dev):
