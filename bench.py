@@ -325,8 +325,8 @@ def oracle_sample_check(ls, model, sd, x_batch, n_set, n_take=4):
         m = R.sequential_match(ca["z_inv"], cb["z_inv"])["matches0"]
         Rk, tk, _ = R.kabsch(ca["z_so3"] + ca["t"], (cb["z_so3"] + cb["t"])[m])
     rel = lambda u, v: ((u.cpu() - v).reshape(u.shape[0], -1).abs().amax(1) / v.reshape(v.shape[0], -1).abs().amax(1))
-    err = torch.stack([rel(out["ref_codes"][k], ca[k]) for k in ("z_so3", "z_inv", "s", "t")] +
-                      [rel(out["rescan_codes"][k], cb[k]) for k in ("z_so3", "z_inv", "s", "t")]).amax(0)
+    err = torch.cat([torch.stack([rel(out[side][k], c[k]) for k in ("z_so3", "z_inv", "s", "t")]).amax(0)
+                     for side, c in (("ref_codes", ca), ("rescan_codes", cb))])   # per instance, 2 * n_take
     return {"instances": 2 * n_take, "matches_equal": bool(torch.equal(out["matches"]["matches0"].cpu(), m)),
             "codes_within_1e-4": int((err < 1e-4).sum()), "codes_max_rel_err": float(err.max()),
             "R_max_abs_err": float((out["R"].cpu() - Rk).abs().max())}

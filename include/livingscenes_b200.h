@@ -161,7 +161,7 @@ LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 pa
 /* 2 (default): persistent warp-specialised tcgen05 GEMM (bulk-TMA fed, double-buffered TMEM); 1: the round-1
  * one-CTA-per-tile kernel (kept for A/B measurements).  Process-global, like the other ls_set_* switches. */
 LS_API int ls_set_gemm_variant(int32_t variant);
-/* Table bytes per wave of the per-layer {point-level table GEMMs -> EdgeConv} schedule (default 28 MiB, env LS_WAVE_MB):
+/* Table bytes per wave of the per-layer {point-level table GEMMs -> EdgeConv} schedule (default 0 = off, env LS_WAVE_MB; measured slower on B200, see profiles/r02):
  * a layer's batch is processed in waves of that many bytes of gather tables, two table slots alternating, so that
  * the tables are consumed out of L2 instead of HBM.  0: one launch per layer for the whole batch.  Results do not
  * depend on the setting. */
@@ -223,6 +223,18 @@ LS_API int ls_seq_match(const float* z0, const float* z1, int32_t dim, const int
 LS_API int ls_mutual_nn(const float* z0, const float* z1, int32_t dim, const int32_t* off0_host,
                  const int32_t* off1_host, int32_t n_pairs, int64_t* matches0, int64_t* matches1,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* sim3_seq_matcher / eq_seq_matcher (matcher_new.py:142-230) for ONE scene pair: the greedy rounds of ls_seq_match on
+ * score = cos / (res + 1e-5) (score_mode 1) or 1 / (res + 1e-5) (score_mode 2); res [n,m] = mean Kabsch residual of
+ * the equivariant codes of every (src, tgt) pair (ls_kabsch_batched on the n*m pairs).  Workspace as ls_seq_match. */
+LS_API int ls_seq_match_scored(const float* z0, const float* z1, int32_t dim, int32_t n, int32_t m, const float* res,
+                        int32_t score_mode, int64_t* matches0, int64_t* matches1, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* sinkhorn_matcher (matcher_new.py:11-71) for ONE scene pair: cosine scores / sqrt(dim), log-space optimal transport
+ * with a dustbin (alpha), `iters` iterations (reference: 100, alpha 1, threshold 0), mutual arg-max + exp(score) >
+ * match_threshold.  n, m <= ~230 (the coupling matrix lives in shared memory).  Workspace as ls_seq_match. */
+LS_API int ls_sinkhorn_match(const float* z0, const float* z1, int32_t dim, int32_t n, int32_t m, int32_t iters,
+                      float alpha, float match_threshold, int64_t* matches0, int64_t* matches1, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pose: kabsch_transformation_estimation (lib_more/pose_estimation.py:29-121)

@@ -11,7 +11,8 @@ extension or with CPU tensors raises.
 from . import _lib  # noqa: F401
 from .decoder import DeepSDF_Decoder, FieldWrapper
 from .encoder import VecDGCNN_att
-from .matcher_new import nn_matcher, nn_matcher_batched, sequential_matcher, sequential_matcher_batched
+from .matcher_new import (eq_seq_matcher, nn_matcher, nn_matcher_batched, sequential_matcher, sequential_matcher_batched,
+                          sim3_seq_matcher, sinkhorn_matcher)
 from .model_utils import Shape_Prior, extract_checkpoint, slice_code_dict
 from .more_solver import More_Solver
 from .ops import farthest_point_sample, knn_points, sample_farthest_points, vn_linear

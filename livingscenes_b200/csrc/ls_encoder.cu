@@ -113,14 +113,16 @@ int small_tc_min() {
     }();
     return v;
 }
-// Wave scheduling of {table GEMMs -> EdgeConv}: the point-level gather tables of a layer are 1.6-5.5 MB per instance
-// (19.5 MB over the six layers).  Written for the whole batch they leave L2 long before the EdgeConv reads them back
-// (round 1: 4.96 GB written + ~6 GB re-read per 256-instance step).  A wave is as many instances as fit g_wave_bytes
-// of tables; two table slots alternate, so the GEMM of wave w+1 overlaps the EdgeConv of wave w and the slot lines
-// are overwritten while still dirty in the 126 MB L2 instead of travelling to HBM and back.  0 disables.
+// Wave scheduling of {table GEMMs -> EdgeConv} (OFF by default; ls_set_wave_bytes / LS_WAVE_MB): the point-level gather
+// tables of a layer are 1.6-5.5 MB per instance (19.5 MB over the six layers); written for the whole batch they leave
+// L2 long before the EdgeConv reads them back.  A wave is as many instances as fit g_wave_bytes of tables; two table
+// slots alternate, so the GEMM of wave w+1 overlaps the EdgeConv of wave w and the slot stays dirty in L2.
+// MEASURED (profiles/r02/experiments.md): at these table sizes an L2-sized wave is only 7-25 instances, the per-wave
+// launches run at a fraction of the GPU and the step gets 37 % SLOWER (11.3 -> 15.4 ms at 28 MB, 22.8 ms at 14 MB),
+// so the whole batch stays one launch per layer.  The schedule is kept, result-invariant and tested, for larger L2s.
 long long g_wave_bytes = [] {
     const char* e = getenv("LS_WAVE_MB");
-    return (long long)(e ? atof(e) : 28.0) * (1LL << 20);
+    return (long long)(e ? atof(e) : 0.0) * (1LL << 20);
 }();
 bool g_use_knn_tc = true;      // tensor-core candidate filter for the larger source sets
 float g_knn_tc_kappa_scale = 1.f;

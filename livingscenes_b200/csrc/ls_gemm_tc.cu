@@ -31,7 +31,10 @@
 //               warps 0-3  epilogue: tcgen05.ld of accumulator buffer i while the MMAs of tile i+1 fill buffer
 //                          i^1 (2 x 128 TMEM columns).
 //               Rings: 3 operand stages (32 KB each), 4 raw stages (8 KB each); no __syncthreads in the tile loop.
+#include <cuda.h>
+
 #include <atomic>
+#include <cstdlib>
 
 #include "ls_common.cuh"
 
@@ -337,9 +340,20 @@ struct G2Shared {
     uint32_t tmem_base;
 };
 
+// one TMA tensor request: box {128 columns, 16 k rows, 1 instance} of the activation tensor -> smem [16][128]
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// tmap: activations as a 3-D tensor (n, k, instance) -- see make_act_map.  tile_per_b = column tiles per instance.
 template <bool PM>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, const float* __restrict__ wpk, int n_kb, int n_mt,
-                                                            int n_tiles) {
+                                                            int n_tiles, const __grid_constant__ CUtensorMap tmap,
+                                                            int tile_per_b) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     G2Shared& sh = *reinterpret_cast<G2Shared*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -374,31 +388,21 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
     const uint32_t tmem = sh.tmem_base;
 
     if (w == G2_PROD_WARP) {
-        // ================================================================ producer: bulk copies
+        // ================================================================ producer: TMA (tensor + bulk) copies
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int mt = tile % n_mt;
-            const long long c0 = (long long)(tile / n_mt) * TN;
-            const long long c_end = (c0 + TN < ncols) ? c0 + TN : ncols;
             const float* wtile = wpk + (size_t)mt * n_kb * (2 * A_STAGE_FLOATS);
+            const int ct = tile / n_mt, tb = ct / tile_per_b, tn0 = (ct - tb * tile_per_b) * TN;
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                // raw activation rows of this k-block: row k of the tile is contiguous per instance
+                // raw activation tile of this k-block: ONE tensor request (rows k >= K and columns past the end are
+                // zero-filled by the TMA unit; the transaction count is always the full box)
                 const int r = it % G2_RS;
                 if (it >= G2_RS) mbar_wait(&sh.raw_empty[r], ((it / G2_RS) - 1) & 1);
-                const int k_rows = (a.K - kb * TKB) < TKB ? (a.K - kb * TKB) : TKB;
-                if (lane == 0) mbar_arrive_expect_tx(&sh.raw_full[r], (uint32_t)((long long)k_rows * (c_end - c0) * 4));
-                __syncwarp();
-                if (lane < k_rows) {
-                    const long long k = (long long)kb * TKB + lane;
-                    long long j = c0;
-                    while (j < c_end) {
-                        const long long bb = j / a.n_per_b, n = j - bb * a.n_per_b;
-                        long long len = (long long)a.n_per_b - n;
-                        if (len > c_end - j) len = c_end - j;
-                        bulk_g2s(&sh.raw[r][lane][j - c0], a.X + bb * a.x_sb + k * a.x_sk + n, (uint32_t)(len * 4),
-                                 &sh.raw_full[r]);
-                        j += len;
-                    }
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&sh.raw_full[r], TKB * TN * 4);
+                    tma_load_3d(&sh.raw[r][0][0], &tmap, tn0, kb * TKB, tb, &sh.raw_full[r]);
                 }
                 // weight image of (m-tile, k-block): one contiguous 16 KB block (hi then lo)
                 const int s = it % G2_S;
@@ -448,8 +452,6 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
         const int kc = w - G2_XF_WARP0;  // k-core (4 k rows) owned by this warp
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long c0 = (long long)(tile / n_mt) * TN;
-            const bool col_ok = c0 + lane * 4 < ncols;  // ncols % 4 == 0: a 4-column group is all in or all out
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
                 const int r = it % G2_RS;
                 mbar_wait(&sh.raw_full[r], (it / G2_RS) & 1);
@@ -457,8 +459,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
                     const int kl = kc * 4 + rr;
-                    v[rr] = (col_ok && kb * TKB + kl < a.K) ? *reinterpret_cast<const float4*>(&sh.raw[r][kl][lane * 4])
-                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[rr] = *reinterpret_cast<const float4*>(&sh.raw[r][kl][lane * 4]);  // out-of-range elements are TMA zero fill
                 }
                 const int s = it % G2_S;
                 if (it >= G2_S) mbar_wait(&sh.empty[s], ((it / G2_S) - 1) & 1);
@@ -625,7 +626,11 @@ bool gemm_tc_supported(const GemmArgs& a) {
     return true;
 }
 
-int g_gemm_variant = 2;  // 2: persistent warp-specialised k_gemm_tc2; 1: round-1 k_gemm_tc
+// 2: persistent warp-specialised k_gemm_tc2; 1: round-1 k_gemm_tc (env LS_GEMM_VARIANT for A/B runs)
+int g_gemm_variant = [] {
+    const char* e = getenv("LS_GEMM_VARIANT");
+    return (e && atoi(e) == 1) ? 1 : 2;
+}();
 
 static int sm_count() {
     static std::atomic<int> cached[64];
@@ -639,6 +644,50 @@ static int sm_count() {
     return v;
 }
 
+// The persistent kernel feeds its activations with ONE TMA tensor request per (tile, k-block): the activation tensor
+// X[b*x_sb + k*x_sk + n] must be expressible as a tiled tensor map whose 128-column boxes never straddle instances:
+// either the columns of consecutive instances are contiguous (x_sb == n_per_b: the SDF decoder's feature-major
+// layout -> one flat column axis), or n_per_b is a multiple of 128.  Other shapes (3 N = 96 columns per instance in
+// encoder layers 5-6 and the head) and launches with few tiles run the per-tile kernel, which is faster there.
+static bool gemm_v2_geometry(const GemmArgs& a) { return a.x_sb == a.n_per_b || a.n_per_b % TN == 0; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<void*> cached{nullptr};
+    void* f = cached.load(std::memory_order_acquire);
+    if (f == nullptr) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        cached.store(f, std::memory_order_release);
+    }
+    return reinterpret_cast<EncodeTiledFn>(f);
+}
+
+static int make_act_map(const GemmArgs& a, CUtensorMap* map, int* tile_per_b) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    LS_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    const bool flat = a.x_sb == a.n_per_b;  // one contiguous column axis over all instances
+    const cuuint64_t n0 = flat ? (cuuint64_t)a.B * a.n_per_b : (cuuint64_t)a.n_per_b;
+    const cuuint64_t nb = flat ? 1 : (cuuint64_t)a.B;
+    const cuuint64_t dims[3] = {n0, (cuuint64_t)a.K, nb};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.x_sk * sizeof(float), (cuuint64_t)(flat ? n0 : a.x_sb) * sizeof(float)};
+    const cuuint32_t box[3] = {TN, TKB, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.X), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return LS_ERR_CUDA;
+    }
+    *tile_per_b = (int)((n0 + TN - 1) / TN);
+    return LS_OK;
+}
+
 int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
     LS_REQUIRE(packed != nullptr, "gemm_tc: packed weights missing");
     LS_REQUIRE(gemm_tc_supported(a), "gemm_tc: unsupported activation geometry");
@@ -650,7 +699,8 @@ int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
     const int n_kb = (a.K + TKB - 1) / TKB;
     // the dynamic shared-memory opt-in is per device: set it on every launch (cheap, legal under stream capture)
     // instead of caching a process-wide flag that a second device in the same process would never see
-    if (g_gemm_variant == 1) {
+    const long long tiles_all = ((ncols + TN - 1) / TN) * ((a.R + TM - 1) / TM);
+    if (g_gemm_variant == 1 || !gemm_v2_geometry(a) || tiles_all < 2LL * sm_count()) {
         dim3 grid((unsigned)((ncols + TN - 1) / TN), (unsigned)((a.R + TM - 1) / TM));
         const size_t smem = sizeof(TcShared) + 128;
         if (a.point_major) {
@@ -667,14 +717,18 @@ int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
     const int n_mt = (a.R + TM - 1) / TM;
     LS_REQUIRE(n_ct * n_mt < (1LL << 31), "gemm_tc: too many tiles");
     const int n_tiles = (int)(n_ct * n_mt);
+    CUtensorMap tmap;
+    int tile_per_b = 0;
+    int rc = make_act_map(a, &tmap, &tile_per_b);
+    if (rc != LS_OK) return rc;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     const size_t smem = sizeof(G2Shared) + 128;
     if (a.point_major) {
         LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gemm_tc2<true><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles);
+        k_gemm_tc2<true><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles, tmap, tile_per_b);
     } else {
         LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gemm_tc2<false><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles);
+        k_gemm_tc2<false><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles, tmap, tile_per_b);
     }
     LS_CHECK_LAUNCH("k_gemm_tc2");
     return LS_OK;

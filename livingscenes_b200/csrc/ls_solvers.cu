@@ -95,7 +95,7 @@ __device__ void normalize_and_score(const float* z0, const float* z1, int n, int
 __global__ void __launch_bounds__(1024) k_seq_match(const float* __restrict__ z0, const float* __restrict__ z1,
                                                     int dim, const PairTable tab, float* __restrict__ wsf,
                                                     int64_t* __restrict__ m0, int64_t* __restrict__ m1, int stage_off,
-                                                    int stage_floats) {
+                                                    int stage_floats, const float* __restrict__ res, int score_mode) {
     __shared__ float redf[32];
     __shared__ int redi[32];
     extern __shared__ unsigned char alive[];  // [n] rows then [m] cols
@@ -119,6 +119,15 @@ __global__ void __launch_bounds__(1024) k_seq_match(const float* __restrict__ z0
                        ? reinterpret_cast<float*>(alive + stage_off)
                        : nullptr;
     normalize_and_score(z0 + (size_t)o0 * dim, z1 + (size_t)o1 * dim, n, m, dim, an, bn, S, stage);
+    if (res != nullptr) {
+        // sim3_seq_matcher / eq_seq_matcher (matcher_new.py:142-230): the cosine score is divided by (mode 1), or
+        // replaced by the inverse of (mode 2), the mean Kabsch residual of the pair's equivariant codes
+        for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
+            const float r = res[e] + 1e-5f;
+            S[e] = score_mode == 1 ? S[e] / r : 1.f / r;
+        }
+        __syncthreads();
+    }
     const int rounds = min(n, m);
     if (n <= 32 && m <= 32) {
         // Small scenes (the common case: <= 32 instances per scan): one warp holds the whole score matrix in
@@ -651,6 +660,111 @@ __global__ void __launch_bounds__(ICP_THREADS) k_icp(const IcpArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ Sinkhorn matcher
+// sinkhorn_matcher (matcher_new.py:11-71): cosine scores / sqrt(desc_dim), log-space optimal transport with a
+// dustbin row/column (alpha = 1), `iters` Sinkhorn iterations, then mutual arg-max on the [n,m] block with the
+// exp(score) > threshold test.  One CTA; the (n+1) x (m+1) coupling matrix lives in shared memory.
+struct SinkArgs {
+    const float* z0;
+    const float* z1;
+    int n, m, dim, iters;
+    float alpha, thr, inv_sqrt_dim;
+    float* ws;  // normalised rows + raw scores (pair_ws_floats)
+    int64_t *m0, *m1;
+};
+
+__device__ __forceinline__ float lse_finish(float mx, float sum) { return mx + logf(sum); }
+
+__global__ void __launch_bounds__(1024) k_sinkhorn_match(const SinkArgs a) {
+    extern __shared__ float sm[];
+    const int n = a.n, m = a.m, ld = m + 1;
+    float* Z = sm;                       // [(n+1)][(m+1)]
+    float* u = Z + (size_t)(n + 1) * ld;  // [n+1]
+    float* v = u + (n + 1);               // [m+1]
+    int* best = reinterpret_cast<int*>(v + (m + 1));  // [n] then [m]
+    float* bval = reinterpret_cast<float*>(best + n + m);  // [n]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* an = a.ws;
+    float* bn = an + (size_t)n * a.dim;
+    float* S = bn + (size_t)m * a.dim;
+    normalize_and_score(a.z0, a.z1, n, m, a.dim, an, bn, S);
+    for (int e = threadIdx.x; e < (n + 1) * ld; e += blockDim.x) {
+        const int i = e / ld, j = e - i * ld;
+        Z[e] = (i < n && j < m) ? S[i * m + j] * a.inv_sqrt_dim : a.alpha;
+    }
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) u[i] = 0.f;
+    for (int j = threadIdx.x; j <= m; j += blockDim.x) v[j] = 0.f;
+    __syncthreads();
+    // log_mu = [norm]*n + [log(m) + norm], log_nu = [norm]*m + [log(n) + norm], norm = -log(n + m)   (:30-33)
+    const float norm = -logf((float)(n + m));
+    const float mu_last = logf((float)m) + norm, nu_last = logf((float)n) + norm;
+    for (int it = 0; it < a.iters; ++it) {
+        // u = log_mu - logsumexp_j(Z + v)
+        for (int i = w; i <= n; i += nw) {
+            float mx = -FLT_MAX;
+            for (int j = lane; j <= m; j += 32) mx = fmaxf(mx, Z[i * ld + j] + v[j]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int j = lane; j <= m; j += 32) sum += expf(Z[i * ld + j] + v[j] - mx);
+            sum = warp_sum(sum);
+            if (lane == 0) u[i] = (i < n ? norm : mu_last) - lse_finish(mx, sum);
+        }
+        __syncthreads();
+        // v = log_nu - logsumexp_i(Z + u)
+        for (int j = w; j <= m; j += nw) {
+            float mx = -FLT_MAX;
+            for (int i = lane; i <= n; i += 32) mx = fmaxf(mx, Z[i * ld + j] + u[i]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int i = lane; i <= n; i += 32) sum += expf(Z[i * ld + j] + u[i] - mx);
+            sum = warp_sum(sum);
+            if (lane == 0) v[j] = (j < m ? norm : nu_last) - lse_finish(mx, sum);
+        }
+        __syncthreads();
+    }
+    // scores = Z + u + v - norm on the [n,m] block; row / column arg-max (first index on ties)
+    for (int i = w; i < n; i += nw) {
+        float bv = -FLT_MAX;
+        int bj = 0x7fffffff;
+        for (int j = lane; j < m; j += 32) {
+            const float x = Z[i * ld + j] + u[i] + v[j] - norm;
+            if (x > bv) { bv = x; bj = j; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const int oj = __shfl_xor_sync(FULL, bj, o);
+            if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+        }
+        if (lane == 0) { best[i] = bj; bval[i] = bv; }
+    }
+    for (int j = w; j < m; j += nw) {
+        float bv = -FLT_MAX;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < n; i += 32) {
+            const float x = Z[i * ld + j] + u[i] + v[j] - norm;
+            if (x > bv) { bv = x; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) best[n + j] = bi;
+    }
+    __syncthreads();
+    // mutual check + score threshold (:57-66)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool valid0 = best[n + best[i]] == i && expf(bval[i]) > a.thr;
+        a.m0[i] = valid0 ? best[i] : -1;
+    }
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int i = best[n + j];
+        const bool mutual1 = best[i] == j;
+        const bool valid0 = best[n + best[i]] == i && expf(bval[i]) > a.thr;
+        a.m1[j] = (mutual1 && valid0) ? i : -1;
+    }
+}
+
 int fill_table(const int32_t* off0, const int32_t* off1, int first, int count, int dim, size_t ws_base,
                PairTable& tab, size_t& ws_end, int& max_nm, int& max_n_plus_m) {
     tab.n_pairs = count;
@@ -676,7 +790,8 @@ int fill_table(const int32_t* off0, const int32_t* off1, int first, int count, i
 
 template <bool SEQ>
 int run_match(const float* z0, const float* z1, int dim, const int32_t* off0, const int32_t* off1, int n_pairs,
-              int64_t* m0, int64_t* m1, void* ws, size_t ws_bytes, cudaStream_t st) {
+              int64_t* m0, int64_t* m1, void* ws, size_t ws_bytes, cudaStream_t st, const float* res = nullptr,
+              int score_mode = 0) {
     LS_REQUIRE(z0 && z1 && off0 && off1 && m0 && m1, "null pointer");
     LS_REQUIRE(n_pairs >= 0 && dim >= 1, "bad sizes");
     size_t ws_off = 0;
@@ -708,7 +823,7 @@ int run_match(const float* z0, const float* z1, int dim, const int32_t* off0, co
             if (smem > 48 * 1024)
                 LS_CHECK_CUDA(cudaFuncSetAttribute(k_seq_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_seq_match<<<count, threads, smem, st>>>(z0, z1, dim, tab, static_cast<float*>(ws), m0, m1, stage_off,
-                                                      stage_floats);
+                                                      stage_floats, res, score_mode);
             LS_CHECK_LAUNCH("k_seq_match");
         } else {
             const size_t smem = (size_t)max_npm * sizeof(int) + 16;
@@ -754,6 +869,43 @@ int ls_mutual_nn(const float* z0, const float* z1, int32_t dim, const int32_t* o
     LS_REQUIRE(dim <= 256, "descriptor dimension above 256 is not supported by ls_match_workspace_bytes");
     return run_match<false>(z0, z1, dim, off0_host, off1_host, n_pairs, matches0, matches1, workspace,
                             workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int ls_seq_match_scored(const float* z0, const float* z1, int32_t dim, int32_t n, int32_t m, const float* res,
+                        int32_t score_mode, int64_t* matches0, int64_t* matches1, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    LS_REQUIRE(dim <= 256, "descriptor dimension above 256 is not supported by ls_match_workspace_bytes");
+    LS_REQUIRE(res != nullptr && (score_mode == 1 || score_mode == 2), "score_mode must be 1 (sim3_seq) or 2 (eq_seq)");
+    const int32_t off0[2] = {0, n}, off1[2] = {0, m};
+    return run_match<true>(z0, z1, dim, off0, off1, 1, matches0, matches1, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream), res, score_mode);
+}
+
+int ls_sinkhorn_match(const float* z0, const float* z1, int32_t dim, int32_t n, int32_t m, int32_t iters, float alpha,
+                      float match_threshold, int64_t* matches0, int64_t* matches1, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    LS_REQUIRE(z0 && z1 && matches0 && matches1 && workspace, "null pointer");
+    LS_REQUIRE(n >= 1 && m >= 1 && dim >= 1 && dim <= 256 && iters >= 0, "bad sizes");
+    LS_REQUIRE(pair_ws_floats(n, m, dim) * sizeof(float) <= workspace_bytes, "sinkhorn workspace too small");
+    const size_t smem = sizeof(float) * ((size_t)(n + 1) * (m + 1) + (n + 1) + (m + 1) + n) + sizeof(int) * (size_t)(n + m) + 16;
+    LS_REQUIRE(smem <= 220 * 1024, "sinkhorn: the (n+1) x (m+1) coupling matrix must fit shared memory (n, m <= ~230)");
+    SinkArgs a{};
+    a.z0 = z0;
+    a.z1 = z1;
+    a.n = n;
+    a.m = m;
+    a.dim = dim;
+    a.iters = iters;
+    a.alpha = alpha;
+    a.thr = match_threshold;
+    a.inv_sqrt_dim = 1.f / sqrtf((float)dim);
+    a.ws = static_cast<float*>(workspace);
+    a.m0 = matches0;
+    a.m1 = matches1;
+    LS_CHECK_CUDA(cudaFuncSetAttribute(k_sinkhorn_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_sinkhorn_match<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
+    LS_CHECK_LAUNCH("k_sinkhorn_match");
+    return LS_OK;
 }
 
 int ls_kabsch_batched(const float* x1, const float* x2, const float* weights, int32_t b, int32_t n,

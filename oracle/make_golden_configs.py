@@ -123,12 +123,50 @@ def c5(sp, sd, x, code):
                         t=_np(code["t"]), shell=_np(shell))
 
 
+def matchers2():
+    """Secondary matchers (matcher_new.py:45-71,142-230) run by the reference's own functions on the C3 codes and on
+    seeded random cases.  ``sinkhorn_matcher`` hard-codes ``.cuda()`` for its alpha scalar: patched to a no-op here."""
+    from unittest import mock
+
+    mods = ref_loader.load()
+    g3 = dict(np.load(os.path.join(OUT, "c3_pair_shipped.npz")))
+    gen = torch.Generator().manual_seed(99)
+    cases = [({"z_inv": torch.from_numpy(g3["za_inv"]), "z_so3": torch.from_numpy(g3["za_so3"])},
+              {"z_inv": torch.from_numpy(g3["zb_inv"]), "z_so3": torch.from_numpy(g3["zb_so3"])})]
+    for n, m in ((7, 9), (12, 5), (20, 20)):
+        za = {"z_inv": torch.randn(n, 256, generator=gen), "z_so3": torch.randn(n, 256, 3, generator=gen)}
+        perm = torch.randperm(max(n, m), generator=gen)[:m] % n
+        Rr = S.random_rotations(m, 5 + n)
+        zb = {"z_inv": za["z_inv"][perm] + 0.3 * torch.randn(m, 256, generator=gen),
+              "z_so3": za["z_so3"][perm] @ Rr.transpose(1, 2) + 0.05 * torch.randn(m, 256, 3, generator=gen)}
+        cases.append((za, zb))
+    out = {"n_cases": np.int64(len(cases))}
+    with mock.patch.object(torch.Tensor, "cuda", lambda self, *a, **k: self):
+        for ci, (za, zb) in enumerate(cases):
+            sk = mods.matcher_new.sinkhorn_matcher(za["z_inv"].T[None], zb["z_inv"].T[None])
+            s3 = mods.matcher_new.sim3_seq_matcher(za, zb)
+            eq = mods.matcher_new.eq_seq_matcher(za, zb)
+            sk2 = R.sinkhorn_match(za["z_inv"].T[None], zb["z_inv"].T[None])
+            s32, eq2 = R.residual_seq_match(za, zb, True), R.residual_seq_match(za, zb, False)
+            for k in ("matches0", "matches1"):
+                assert torch.equal(sk[k].reshape(-1), sk2[k].reshape(-1)), ("sinkhorn", ci, k)
+                assert torch.equal(s3[k], s32[k]), ("sim3_seq", ci, k)
+                assert torch.equal(eq[k], eq2[k]), ("eq_seq", ci, k)
+            for nm, t in (("a_inv", za["z_inv"]), ("a_so3", za["z_so3"]), ("b_inv", zb["z_inv"]), ("b_so3", zb["z_so3"])):
+                out[f"c{ci}_{nm}"] = _np(t)
+            for nm, r in (("sk", sk), ("s3", s3), ("eq", eq)):
+                out[f"c{ci}_{nm}0"], out[f"c{ci}_{nm}1"] = _np(r["matches0"].reshape(-1)), _np(r["matches1"].reshape(-1))
+            print(f"[matchers2] case {ci}: sinkhorn matched {int((sk['matches0'] >= 0).sum())}, sim3_seq/eq_seq agree with "
+                  f"sequential on {int((s3['matches0'] == eq['matches0']).sum())}/{len(s3['matches0'])}")
+    np.savez_compressed(os.path.join(OUT, "matchers2_cases.npz"), **out)
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     assert ref_loader.available() and ref_loader.checkpoint_available(), "needs /root/reference"
     only = sys.argv[1:]
     sd = ref_loader.shipped_state_dict()
-    sp = ref_loader.shape_prior(None)
+    sp = ref_loader.shape_prior(None) if (not only or set(only) & {"c2", "c3", "c5"}) else None
     t0 = time.time()
     x = code = None
     if not only or "c2" in only or "c5" in only:
@@ -140,6 +178,8 @@ def main():
     if not only or "c3" in only:
         c3(sp, sd)
         print(f"c3 done {time.time() - t0:.0f}s")
+    if not only or "matchers2" in only:
+        matchers2()
     for f in sorted(os.listdir(OUT)):
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f)) / 1024:.0f} KB")
 

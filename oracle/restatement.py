@@ -225,8 +225,8 @@ def sequential_match(m0: torch.Tensor, m1: torch.Tensor) -> dict:
     b = m1 / m1.norm(dim=1, keepdim=True).clamp_min(EPS_NRM)
     n, m = a.shape[0], b.shape[0]
     rows, cols = list(range(n)), list(range(m))
-    out0 = torch.full((n,), -1, dtype=torch.int64)
-    out1 = torch.full((m,), -1, dtype=torch.int64)
+    out0 = torch.full((n,), -1, dtype=torch.int64, device=m0.device)
+    out1 = torch.full((m,), -1, dtype=torch.int64, device=m0.device)
     S = a @ b.T
     for _ in range(min(n, m)):
         S = S / (S.max() + 1e-5)
@@ -250,10 +250,10 @@ def mutual_nn_match(desc0: torch.Tensor, desc1: torch.Tensor) -> dict:
     f0 = sim.argmax(dim=2)
     f1 = sim.argmax(dim=1)
     n, m = f0.shape[1], f1.shape[1]
-    ok0 = torch.gather(f1, 1, f0) == torch.arange(n)[None]
+    ok0 = torch.gather(f1, 1, f0) == torch.arange(n, device=f0.device)[None]
     m0 = torch.where(ok0, f0, torch.full_like(f0, -1))
     back = torch.gather(m0, 1, f1)
-    ok1 = back == torch.arange(m)[None]
+    ok1 = back == torch.arange(m, device=f0.device)[None]
     m1 = torch.where(ok1, f1, torch.full_like(f1, -1))
     return {"matches0": m0.squeeze(), "matches1": m1.squeeze()}
 
@@ -264,7 +264,7 @@ def kabsch(x1: torch.Tensor, x2: torch.Tensor, weights: Optional[torch.Tensor] =
     """Weighted Kabsch (lib_more/pose_estimation.py:29-121): x1, x2 [b,n,3] ->
     R [b,3,3], t [b,3,1], residual norms [b,n].  Orientation fix R = V diag(1,1,det(V U^T)) U^T."""
     b, n, _ = x1.shape
-    w = torch.ones(b, n, dtype=x1.dtype) if weights is None else weights
+    w = torch.ones(b, n, dtype=x1.dtype, device=x1.device) if weights is None else weights
     if normalize_w:
         w = w / (w.sum(dim=1, keepdim=True) + eps)
     w = w.unsqueeze(2)
@@ -321,4 +321,67 @@ def sdf_decode(Wd, query: torch.Tensor, code: dict, latent_in=(4,)) -> torch.Ten
 # --------------------------------------------------------------------------- synthetic inputs / weights
 # The seeded generators live in the package (livingscenes_b200/synthetic.py: pure-torch CPU helpers shared by
 # bench.py, scripts/ and the tests) so that nothing outside tests / smoke / the CPU-baseline leg imports oracle/.
+
+
+# --------------------------------------------------------------------------- secondary matchers
+def sinkhorn_match(desc0: torch.Tensor, desc1: torch.Tensor, iters: int = 100, alpha: float = 1.0,
+                   match_threshold: float = 0.0) -> dict:
+    """sinkhorn_matcher (matcher_new.py:11-71): desc [1,D,n] / [1,D,m]; cosine scores / sqrt(D), log-space optimal
+    transport with a dustbin row and column (alpha), mutual arg-max on the [n,m] block, exp(score) > threshold."""
+    a = desc0 / desc0.norm(dim=1, keepdim=True).clamp_min(EPS_NRM)
+    b = desc1 / desc1.norm(dim=1, keepdim=True).clamp_min(EPS_NRM)
+    S = torch.einsum("bdn,bdm->bnm", a, b)[0] / math.sqrt(desc0.shape[1])
+    n, m = S.shape
+    Z = torch.full((n + 1, m + 1), float(alpha), dtype=S.dtype, device=S.device)
+    Z[:n, :m] = S
+    norm = -math.log(n + m)
+    log_mu = torch.full((n + 1,), norm, dtype=S.dtype, device=S.device)
+    log_nu = torch.full((m + 1,), norm, dtype=S.dtype, device=S.device)
+    log_mu[n] = math.log(m) + norm
+    log_nu[m] = math.log(n) + norm
+    u, v = torch.zeros_like(log_mu), torch.zeros_like(log_nu)
+    for _ in range(iters):
+        u = log_mu - torch.logsumexp(Z + v[None, :], dim=1)
+        v = log_nu - torch.logsumexp(Z + u[:, None], dim=0)
+    Z = Z + u[:, None] + v[None, :] - norm
+    blk = Z[:n, :m]
+    v0, i0 = blk.max(dim=1)
+    i1 = blk.max(dim=0).indices
+    ar_n, ar_m = torch.arange(n, device=S.device), torch.arange(m, device=S.device)
+    mutual0 = i1[i0] == ar_n
+    mutual1 = i0[i1] == ar_m
+    valid0 = mutual0 & (torch.where(mutual0, v0.exp(), torch.zeros_like(v0)) > match_threshold)
+    valid1 = mutual1 & valid0[i1]
+    return {"matches0": torch.where(valid0, i0, torch.full_like(i0, -1)),
+            "matches1": torch.where(valid1, i1, torch.full_like(i1, -1))}
+
+
+def residual_seq_match(src_codes: dict, tgt_codes: dict, use_sim: bool) -> dict:
+    """sim3_seq_matcher (use_sim, matcher_new.py:142-185) / eq_seq_matcher (:188-230): the greedy rounds of
+    sequential_match on  cos / (res + 1e-5)  or  1 / (res + 1e-5),  res[i,j] = mean Kabsch residual of the
+    equivariant codes z_so3 src[i] -> tgt[j]."""
+    a = src_codes["z_inv"] / src_codes["z_inv"].norm(dim=1, keepdim=True).clamp_min(EPS_NRM)
+    b = tgt_codes["z_inv"] / tgt_codes["z_inv"].norm(dim=1, keepdim=True).clamp_min(EPS_NRM)
+    n, m = a.shape[0], b.shape[0]
+    res = torch.zeros(n, m, dtype=a.dtype, device=a.device)
+    for i in range(n):
+        _, _, r = kabsch(src_codes["z_so3"][i][None].repeat_interleave(m, dim=0), tgt_codes["z_so3"])
+        res[i] = r.mean(dim=1)
+    S = (a @ b.T) / (res + 1e-5) if use_sim else 1.0 / (res + 1e-5)
+    rows, cols = list(range(n)), list(range(m))
+    out0 = torch.full((n,), -1, dtype=torch.int64, device=a.device)
+    out1 = torch.full((m,), -1, dtype=torch.int64, device=a.device)
+    for _ in range(min(n, m)):
+        S = S / (S.max() + 1e-5)
+        flat = int((S == S.max()).reshape(-1).nonzero()[0, 0])
+        r, c = divmod(flat, S.shape[1])
+        out0[rows[r]] = cols[c]
+        out1[cols[c]] = rows[r]
+        keep_r = [i for i in range(S.shape[0]) if i != r]
+        keep_c = [j for j in range(S.shape[1]) if j != c]
+        S = S[keep_r][:, keep_c]
+        del rows[r], cols[c]
+    return {"matches0": out0, "matches1": out1}
+
+
 from livingscenes_b200.synthetic import random_rotations, random_state_dict, synth_instances  # noqa: E402,F401

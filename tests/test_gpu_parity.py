@@ -417,7 +417,7 @@ def test_encoder_wave_schedule_invariance(dev, oracle_R):
             for k in ("z_so3", "z_inv", "scale", "center"):
                 assert torch.equal(ref[k], r[k]), k
     finally:
-        _lib.set_wave_bytes(28 << 20)
+        _lib.set_wave_bytes(0)
         _lib.set_overlap(True)
         _lib.set_gemm_variant(2)
 
