@@ -34,7 +34,7 @@ extern "C" {
 #define LS_API
 #endif
 
-#define LS_ABI_VERSION 2
+#define LS_ABI_VERSION 3
 #define LS_MAX_LAYERS 8
 #define LS_KNN_K 16          /* num_knn of the shipped model (model_config.yaml:165) */
 #define LS_HEAD_C 16         /* atten_multi_head_c (model_config.yaml:143)           */
@@ -277,6 +277,16 @@ typedef struct ls_decoder_desc {
     int32_t out_dims[12];  /* 768,768,768,255,768,768,768,768,1                                   */
     int32_t in_dims[12];   /* K of each GEMM (un-padded): 257,768,768,768,512,768,768,768,768     */
     const float* w_tc[12]; /* optional: w[l] packed by ls_tc_pack_weights (layers 0..7)                  */
+    /* backward only (ls_sdf_backward; may be NULL for inference): transposed effective weights, row-major
+       [in][out_padded8]: wt[l] for l = 0 (the [inner,|q|] columns: [257][768]), 1,2,3 ([768][255->256]),5,6,7;
+       layer latent_in split into its h rows (wt4_h [255][768]) and its [inner,|q|] rows (wt4_u [257][768]);
+       *_tc = the same packed by ls_tc_pack_weights (optional) */
+    const float* wt[12];
+    const float* wt_tc[12];
+    const float* wt4_h;
+    const float* wt4_u;
+    const float* wt4_h_tc;
+    const float* wt4_u_tc;
 } ls_decoder_desc;
 
 LS_API int ls_sdf_workspace_bytes(const ls_decoder_desc* desc, int32_t B, int32_t M, size_t* bytes);
@@ -285,6 +295,17 @@ LS_API int ls_sdf_workspace_bytes(const ls_decoder_desc* desc, int32_t B, int32_
 LS_API int ls_sdf_decode(const ls_decoder_desc* desc, const float* query, const float* z_so3,
                   const float* z_inv, const float* s, const float* t, int32_t B, int32_t M,
                   float* sdf, void* workspace, size_t workspace_bytes, void* stream);
+
+
+/* Gradients of the SDF query (the reference back-propagates through FieldWrapper / DeepSDF_Decoder with autograd in
+ * More_Solver._solve_pairwise_registration(optim=True), more_solver.py:153-158, and _optimize_code, :210-214).
+ * grad_sdf [B,M] = dLoss/dsdf.  Outputs (each may be NULL): grad_query [B,M,3], grad_z_so3 [B,latent,3],
+ * grad_z_inv [B,latent], grad_s [B], grad_t [B,3] -- written, not accumulated.  B * M <= 131072 per call. */
+LS_API int ls_sdf_backward_workspace_bytes(const ls_decoder_desc* desc, int32_t B, int32_t M, size_t* bytes);
+LS_API int ls_sdf_backward(const ls_decoder_desc* desc, const float* query, const float* z_so3, const float* z_inv,
+                    const float* s, const float* t, int32_t B, int32_t M, const float* grad_sdf,
+                    float* grad_query, float* grad_z_so3, float* grad_z_inv, float* grad_s, float* grad_t,
+                    void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

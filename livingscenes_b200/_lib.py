@@ -63,6 +63,8 @@ class DecoderDesc(C.Structure):
         ("w0_zinv", C.c_void_p), ("w4_zinv", C.c_void_p),
         ("out_dims", C.c_int32 * 12), ("in_dims", C.c_int32 * 12),
         ("w_tc", C.c_void_p * 12),
+        ("wt", C.c_void_p * 12), ("wt_tc", C.c_void_p * 12),
+        ("wt4_h", C.c_void_p), ("wt4_u", C.c_void_p), ("wt4_h_tc", C.c_void_p), ("wt4_u_tc", C.c_void_p),
     ]
 
 
@@ -109,6 +111,9 @@ _PROTOS = {
     "ls_icp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_sdf_workspace_bytes": (C.c_int, [C.POINTER(DecoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_sdf_backward_workspace_bytes": (C.c_int, [C.POINTER(DecoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_sdf_backward": (C.c_int, [C.POINTER(DecoderDesc)] + [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 7 +
+                        [C.c_size_t, C.c_void_p]),
     "ls_sdf_decode": (C.c_int, [C.POINTER(DecoderDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

@@ -122,6 +122,9 @@ struct GemmArgs {
     long long bias_sb, bias_sr;
     int bias_axis;
     int relu;
+    // optional (store mode 0 only): zero the result where mask[same offset as out] <= 0 -- the ReLU derivative of the
+    // decoder's backward pass, with the forward activation as the mask
+    const float* mask;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);       // dispatches to the tcgen05 path when possible
 int launch_gemm_simt(const GemmArgs& a, cudaStream_t st);

@@ -276,7 +276,19 @@ __device__ __forceinline__ void fps_scratch_loop(float4* __restrict__ sb, int N,
         }
     };
     if (t == 0) publish(0, last);
-    for (int j = 1; j < n_out; ++j) {
+    // fewer points than samples: every point is selected once, the remaining slots are padded the way pytorch3d pads
+    // them (index -1, coordinates 0) -- the reference's encode_fps then encodes those zeros as points (model_utils.py:205)
+    const int n_sel = n_out < N ? n_out : N;
+    for (int j = n_sel + t; j < n_out; j += T) {
+        if (sel64) sel64[(size_t)b * n_out + j] = -1;
+        if (out_xyz) {
+            float* o = out_xyz + (size_t)b * 3 * n_out + j;
+            o[0] = 0.f;
+            o[n_out] = 0.f;
+            o[2 * n_out] = 0.f;
+        }
+    }
+    for (int j = 1; j < n_sel; ++j) {
         const float4 lp = sb[last];
         const float lx = lp.x, ly = lp.y, lz = lp.z;
         float bv = -2.f;
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xy
 }
 
 // xyz [B][3][Nmax], mask [B][Nmax] (bytes, non-zero = valid).  n_valid[b] receives the number of valid points; an
-// instance with fewer valid points than n_out repeats point 0 once its points are exhausted (callers check n_valid).
+// instance with fewer valid points than n_out selects all of them and pads with index -1 / zero coordinates (pytorch3d).
 __global__ void __launch_bounds__(1024) k_fps_masked(const float* __restrict__ xyz, const unsigned char* __restrict__ mask,
                                                      int Nmax, int n_out, const int64_t* __restrict__ start,
                                                      float4* __restrict__ scr, int32_t* __restrict__ n_valid,

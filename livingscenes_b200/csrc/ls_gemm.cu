@@ -126,7 +126,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm(const GemmArgs a) {
                     float v = acc[i][j];
                     if (a.bias) v += __ldg(a.bias + b * a.bias_sb + (long long)r * a.bias_sr + (a.bias_axis ? axis : 0));
                     if (a.relu) v = fmaxf(v, 0.f);
-                    a.out[b * a.o_sb + (long long)r * a.o_sr + n] = v;
+                    const long long oo = b * a.o_sb + (long long)r * a.o_sr + n;
+                    if (a.mask && !(__ldg(a.mask + oo) > 0.f)) v = 0.f;
+                    a.out[oo] = v;
                 }
             }
         }

@@ -22,15 +22,15 @@
 //   k_gemm_tc   (round 1) one CTA per tile, operands staged through registers, 2-stage ring, __syncthreads per
 //               k-block.  Kept as the A/B reference (ls_set_gemm_variant(1)).
 //   k_gemm_tc2  (default) persistent, warp-specialised: grid = #SMs, every CTA loops over output tiles;
-//               warp 8     producer: cp.async.bulk (TMA bulk, mbarrier complete_tx) of the 16 KB weight image of
+//               warp 16    producer: cp.async.bulk (TMA bulk, mbarrier complete_tx) of the 16 KB weight image of
 //                          the k-block and of the raw fp32 activation rows (512 B per k row and tile);
-//               warps 4-7  transform: raw [16 k][128 n] tile -> hi/lo TF32 split in the canonical K-major UMMA
+//               warps 4-15 transform (3 groups of 4, k-blocks round robin): raw [16 k][128 n] tile -> hi/lo TF32 split in the canonical K-major UMMA
 //                          image (the 4x4 register transpose of round 1, now smem -> smem);
-//               warp 9     one thread issues the tcgen05.mma's; tcgen05.commit frees the operand stage / publishes
+//               warp 17    one thread issues the tcgen05.mma's; tcgen05.commit frees the operand stage / publishes
 //                          the accumulator;
 //               warps 0-3  epilogue: tcgen05.ld of accumulator buffer i while the MMAs of tile i+1 fill buffer
 //                          i^1 (2 x 128 TMEM columns).
-//               Rings: 3 operand stages (32 KB each), 4 raw stages (8 KB each); no __syncthreads in the tile loop.
+//               Rings: 4 operand stages (32 KB each), 4 raw stages (8 KB each); no __syncthreads in the tile loop.
 #include <cuda.h>
 
 #include <atomic>
@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
                     float val = tile[rr * 33 + lane];
                     if (a.bias) val += __ldg(a.bias + bo + (long long)row * a.bias_sr);
                     if (a.relu) val = fmaxf(val, 0.f);
+                    if (a.mask && !(__ldg(a.mask + base + (long long)row * a.o_sr) > 0.f)) val = 0.f;
                     a.out[base + (long long)row * a.o_sr] = val;
                 }
             }
@@ -312,9 +313,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
 // =====================================================================================================
 // k_gemm_tc2: persistent warp-specialised variant (see the header comment)
 // =====================================================================================================
-constexpr int G2_S = 3, G2_RS = 4;                 // operand stages, raw activation stages
-constexpr int G2_THREADS = 320;                     // warps 0-3 epilogue, 4-7 transform, 8 producer, 9 MMA
-constexpr int G2_XF_WARP0 = 4, G2_PROD_WARP = 8, G2_MMA_WARP = 9;
+constexpr int G2_S = 4, G2_RS = 4;                 // operand stages, raw activation stages
+// The raw -> hi/lo transform of one k-block is a ~600-cycle dependent chain per warp (LDS, split, 8 STS, proxy fence,
+// arrive) against 384 cycles of MMA work per k-block: with one transform group the round-2 profile showed the epilogue
+// and the MMA warp waiting on it (profiles/r02/ncu_gemm_tc2_v2a.txt).  G2_XF_GROUPS groups of 4 warps take the k-blocks
+// round robin, so several k-blocks are transformed concurrently.
+constexpr int G2_XF_GROUPS = 3;
+constexpr int G2_XF_WARP0 = 4, G2_PROD_WARP = 4 + 4 * G2_XF_GROUPS, G2_MMA_WARP = G2_PROD_WARP + 1;
+constexpr int G2_THREADS = 32 * (G2_MMA_WARP + 1);  // warps 0-3 epilogue, 4.. transform groups, producer, MMA
 constexpr int G2_TMEM_COLS = 2 * TN;                // two accumulator buffers
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -449,10 +455,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
         }
     } else if (w >= G2_XF_WARP0) {
         // ================================================================ transform: raw fp32 -> hi/lo K-major images
-        const int kc = w - G2_XF_WARP0;  // k-core (4 k rows) owned by this warp
+        const int kc = (w - G2_XF_WARP0) & 3;   // k-core (4 k rows) owned by this warp
+        const int grp = (w - G2_XF_WARP0) >> 2;  // transform group: handles the k-blocks with it % G2_XF_GROUPS == grp
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                if (it % G2_XF_GROUPS != grp) continue;
                 const int r = it % G2_RS;
                 mbar_wait(&sh.raw_full[r], (it / G2_RS) & 1);
                 float4 v[4];
@@ -555,22 +563,40 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                         }
                     }
                 } else {
-                    // channel-major: transpose the warp's 32 rows x 32 columns so that lanes store consecutive columns
+                    // channel-major.  Bias + ReLU are applied while lane == row (the bias offset of a column is warp
+                    // uniform and rarely changes inside a chunk: one cached load instead of a dependent load per element),
+                    // then the warp's 32 x 32 block is transposed so that lanes store consecutive columns.
                     float* tl = &sh.epi[w][0];
+                    float bcache = 0.f;
+                    long long last_bo = -1;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) tl[lane * 33 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        float val = __uint_as_float(v[j]);
+                        if (a.bias) {
+                            const long long bo = sh.col_bias[cc + j];
+                            if (bo != last_bo) {
+                                bcache = row_ok ? __ldg(a.bias + bo + (long long)r * a.bias_sr) : 0.f;
+                                last_bo = bo;
+                            }
+                            val += bcache;
+                        }
+                        if (a.relu) val = fmaxf(val, 0.f);
+                        tl[lane * 33 + j] = val;
+                    }
                     __syncwarp();
                     const long long base = sh.col_base[cc + lane];
-                    const long long bo = sh.col_bias[cc + lane];
                     if (base >= 0) {
+                        const int nrow = min(32, a.R - (r0 + w * 32));
+                        if (a.mask) {
 #pragma unroll 8
-                        for (int rr = 0; rr < 32; ++rr) {
-                            const int row = r0 + w * 32 + rr;
-                            if (row >= a.R) break;
-                            float val = tl[rr * 33 + lane];
-                            if (a.bias) val += __ldg(a.bias + bo + (long long)row * a.bias_sr);
-                            if (a.relu) val = fmaxf(val, 0.f);
-                            a.out[base + (long long)row * a.o_sr] = val;
+                            for (int rr = 0; rr < nrow; ++rr) {
+                                const long long oo = base + (long long)(r0 + w * 32 + rr) * a.o_sr;
+                                a.out[oo] = __ldg(a.mask + oo) > 0.f ? tl[rr * 33 + lane] : 0.f;
+                            }
+                        } else {
+#pragma unroll 8
+                            for (int rr = 0; rr < nrow; ++rr)
+                                a.out[base + (long long)(r0 + w * 32 + rr) * a.o_sr] = tl[rr * 33 + lane];
                         }
                     }
                     __syncwarp();

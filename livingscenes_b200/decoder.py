@@ -4,8 +4,9 @@ Mirrors ``lib_shape_prior/core/lib/implicit_func/deepsdf_decoder.py:9-123`` (par
 ``lin{0..7}.{bias,weight_g,weight_v}``, ``lin8.{weight,bias}``) and ``model_utils.py:221-263``
 (``FieldWrapper.forward(query, z_none, c, return_sdf=False)``, ``inner_deepsdf`` branch).
 The modules hold parameters; the arithmetic runs in ``ls_sdf_decode`` (C ABI).
-Inference only: back-propagation through the decoder (the reference's ``optim=True`` registration
-and ``_optimize_code``, more_solver.py:118-228) is out of scope.
+Back-propagation to the query points and the code (the reference's ``optim=True`` registration and
+``_optimize_code``, more_solver.py:118-228, use autograd through the decoder) runs in ``ls_sdf_backward``
+behind a ``torch.autograd.Function``; the decoder WEIGHTS get no gradient (inference-time optimisation only).
 """
 from __future__ import annotations
 
@@ -50,6 +51,9 @@ class DeepSDF_Decoder(nn.Module):
         super().__init__()
         if xyz_in_all or use_tanh or latent_dropout:
             raise NotImplementedError("only the shipped decoder configuration is built")
+        if not weight_norm and len(list(norm_layers or ())) > 0:
+            # the reference inserts nn.LayerNorm ("bn{l}") for these layers (deepsdf_decoder.py:59-63): not built
+            raise NotImplementedError("norm_layers without weight_norm (LayerNorm variant) is not built")
         full = [latent_size + pe_dim] + list(dims) + [1]
         self.latent_size, self.pe_dim = latent_size, pe_dim
         self.num_layers = len(full)
@@ -111,8 +115,35 @@ class DeepSDF_Decoder(nn.Module):
             wv = blob[offs[f"w{l}"]:offs[f"w{l}"] + self.out_dims[l] * Kp].view(self.out_dims[l], Kp)[:, :K]
             tc[l] = _lib.tc_pack(wv.contiguous())
             d.w_tc[l] = tc[l].data_ptr()
-        self._packed = {"ver": ver, "blob": blob, "desc": d, "tc": tc}
+        self._packed = {"ver": ver, "blob": blob, "desc": d, "tc": tc, "mats": {l: mats.get(l, eff[l][0].float().cpu())
+                                                                                  for l in range(8)}, "bwd": False}
         return self._packed
+
+    def _pack_backward(self, device) -> dict:
+        """Transposed weights for ``ls_sdf_backward`` (built on first use: inference never pays for them)."""
+        pk = self._pack(device)
+        if pk["bwd"]:
+            return pk
+        d, h3 = pk["desc"], self.out_dims[3]
+        keep = []
+
+        def put(Wt):  # [in][out] -> device copy padded to a multiple of 8 columns + its tcgen05 image
+            K = Wt.shape[1]
+            Kp = (K + 7) // 8 * 8
+            Wp = torch.zeros(Wt.shape[0], Kp)
+            Wp[:, :K] = Wt
+            Wp = Wp.to(device)
+            packed = _lib.tc_pack(Wp[:, :K].contiguous())
+            keep.extend([Wp, packed])
+            return Wp.data_ptr(), packed.data_ptr()
+
+        for l in (0, 1, 2, 3, 5, 6, 7):
+            d.wt[l], d.wt_tc[l] = put(pk["mats"][l].t().contiguous())
+        W4 = pk["mats"][4]  # [H][h3 + L + 1]
+        d.wt4_h, d.wt4_h_tc = put(W4[:, :h3].t().contiguous())
+        d.wt4_u, d.wt4_u_tc = put(W4[:, h3:].t().contiguous())
+        pk["bwd_keep"], pk["bwd"] = keep, True
+        return pk
 
     @torch.no_grad()
     def query(self, query: torch.Tensor, code: dict) -> torch.Tensor:
@@ -141,10 +172,70 @@ class DeepSDF_Decoder(nn.Module):
             ws.record_stream(torch.cuda.current_stream(dev))
         return sdf
 
+    BWD_MAX_COLS = 131072
+
+    @torch.no_grad()
+    def query_backward(self, query, code, grad_sdf, need=(True, True, True, True, True)):
+        """Gradients of ``query`` (the SDF) for dLoss/dsdf = grad_sdf [B,M]: (grad_query [B,M,3], grad_z_so3, grad_z_inv,
+        grad_s [B], grad_t [B,3]); long query lists are chunked and the code gradients summed."""
+        _lib.require_cuda(query, "query")
+        dev = query.device
+        q = query.detach().float().contiguous()
+        B, M, _ = q.shape
+        z_so3 = code["z_so3"].detach().float().contiguous()
+        z_inv = code["z_inv"].detach().float().contiguous()
+        s = code["s"].detach().float().reshape(B).contiguous()
+        t = code["t"].detach().float().reshape(B, 3).contiguous()
+        g = grad_sdf.detach().float().contiguous()
+        Mc = max(1, min(M, self.BWD_MAX_COLS // B))
+        gq = torch.empty(B, M, 3, device=dev)
+        acc = None
+        with torch.cuda.device(dev):
+            pk = self._pack_backward(dev)
+            for m0 in range(0, M, Mc):
+                m1 = min(M, m0 + Mc)
+                qc, gc = q[:, m0:m1].contiguous(), g[:, m0:m1].contiguous()
+                nbytes = C.c_size_t(0)
+                _lib.check(_lib.lib().ls_sdf_backward_workspace_bytes(C.byref(pk["desc"]), B, m1 - m0, C.byref(nbytes)),
+                           "ls_sdf_backward_workspace_bytes")
+                ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+                gqc = torch.empty(B, m1 - m0, 3, device=dev)
+                part = [torch.empty(B, self.latent_size, 3, device=dev), torch.empty(B, self.latent_size, device=dev),
+                        torch.empty(B, device=dev), torch.empty(B, 3, device=dev)]
+                rc = _lib.lib().ls_sdf_backward(C.byref(pk["desc"]), qc.data_ptr(), z_so3.data_ptr(), z_inv.data_ptr(),
+                                                s.data_ptr(), t.data_ptr(), B, m1 - m0, gc.data_ptr(), gqc.data_ptr(),
+                                                part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr(),
+                                                part[3].data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+                _lib.check(rc, "ls_sdf_backward")
+                _lib.launch_count += 1
+                ws.record_stream(torch.cuda.current_stream(dev))
+                gq[:, m0:m1] = gqc
+                acc = part if acc is None else [a + b for a, b in zip(acc, part)]
+        return (gq, *acc)
+
     def forward(self, input, phase="val"):
         raise NotImplementedError(
             "the CUDA decoder never materialises the [B,M,513] input tensor; call FieldWrapper.forward "
             "(query, None, code, return_sdf) as the reference's callers do (model_utils.py:230-263)")
+
+
+class _SDFQuery(torch.autograd.Function):
+    """sdf = decoder(query; z_so3, z_inv, s, t) with the CUDA forward (ls_sdf_decode) and backward (ls_sdf_backward)."""
+
+    @staticmethod
+    def forward(ctx, decoder, query, z_so3, z_inv, s, t):
+        ctx.decoder = decoder
+        ctx.save_for_backward(query, z_so3, z_inv, s, t)
+        return decoder.query(query, {"z_so3": z_so3, "z_inv": z_inv, "s": s, "t": t})
+
+    @staticmethod
+    def backward(ctx, grad_sdf):
+        query, z_so3, z_inv, s, t = ctx.saved_tensors
+        gq, gzs, gzi, gs, gt = ctx.decoder.query_backward(query, {"z_so3": z_so3, "z_inv": z_inv, "s": s, "t": t}, grad_sdf)
+        need = ctx.needs_input_grad
+        return (None, gq.to(query.dtype) if need[1] else None, gzs.reshape(z_so3.shape) if need[2] else None,
+                gzi.reshape(z_inv.shape) if need[3] else None, gs.reshape(s.shape) if need[4] else None,
+                gt.reshape(t.shape) if need[5] else None)
 
 
 class FieldWrapper(nn.Module):
@@ -159,9 +250,12 @@ class FieldWrapper(nn.Module):
         self.decoder_type = decoder_type
 
     def forward(self, query, z_none, c, return_sdf=False):
-        if any(torch.is_tensor(v) and v.requires_grad for v in (query, *c.values())) and torch.is_grad_enabled():
-            raise NotImplementedError("the CUDA SDF decoder is inference-only (no backward); see SURVEY.md 8f rank 4")
-        sdf = self.F.query(query, c).to(query.dtype)
+        if torch.is_grad_enabled() and any(torch.is_tensor(v) and v.requires_grad
+                                           for v in (query, c["z_so3"], c["z_inv"], c["s"], c["t"])):
+            # the reference's optimisation loops differentiate the SDF w.r.t. the query points / the code
+            sdf = _SDFQuery.apply(self.F, query, c["z_so3"], c["z_inv"], c["s"], c["t"]).to(query.dtype)
+        else:
+            sdf = self.F.query(query, c).to(query.dtype)
         if return_sdf:
             return sdf
         return dist.Bernoulli(logits=self.sdf2occ_factor * sdf)

@@ -141,9 +141,8 @@ class Shape_Prior(nn.Module):
         B = batch_pc.shape[0]
         mask = batch_mask.reshape(B, -1)
         n_valid = mask.sum(-1)
-        if int(n_valid.min()) < self.field_input_n:
-            raise ValueError(f"encode_fps: an instance has {int(n_valid.min())} valid points, fewer than the "
-                             f"{self.field_input_n} the encoder samples")
+        # an instance with fewer than field_input_n valid points is accepted like the reference does: pytorch3d's FPS
+        # selects all of its points and pads the sample with zeros, which are then encoded as points
         if n_fps == 1:
             pc, mk, start = batch_pc, mask, None
         else:  # random restarts (model_utils.py:202,205): first index drawn per restart, codes averaged below

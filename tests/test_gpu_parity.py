@@ -322,8 +322,18 @@ def test_encode_fps_random_restarts(dev, oracle_R):
         code1 = oracle_R.encode(sd, torch.cat(subs, 0).transpose(1, 2).contiguous())
     for k in ("z_so3", "z_inv", "s", "t"):
         assert relerr(out1[k].cpu(), code1[k]) < TOL, k
-    with pytest.raises(ValueError):
-        model.encode_fps(pc[:, :, :900].to(dev), torch.ones(B, 1, 900, dtype=torch.bool, device=dev))
+    # fewer valid points than the encoder samples: accepted like the reference -- pytorch3d's FPS selects every
+    # point (FPS order) and pads the sample with zeros, which are encoded as points (model_utils.py:203-207)
+    small = model.encode_fps(pc[:, :, :900].to(dev), torch.ones(B, 1, 900, dtype=torch.bool, device=dev))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        subs = []
+        for b in range(B):
+            s900, _ = ref_fps(pc[b, :, :900].T[None].contiguous(), K=900)
+            subs.append(torch.cat([s900, torch.zeros(1, model.field_input_n - 900, 3)], 1))
+        code_s = oracle_R.encode(sd, torch.cat(subs, 0).transpose(1, 2).contiguous())
+    for k in ("z_so3", "z_inv", "s", "t"):
+        assert relerr(small[k].cpu(), code_s[k]) < TOL, k
 
 
 @pytest.mark.parametrize("N,n_out", [(1024, 512), (2048, 1024), (1000, 77), (5000, 1024), (16, 16)])

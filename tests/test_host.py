@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     handle = _lib.lib()
     for name in declared:
         assert hasattr(handle, name)
-    assert handle.ls_version() == 2
+    assert handle.ls_version() == 3
     # argument validation happens before any CUDA call
     n = ctypes.c_size_t(0)
     assert handle.ls_encoder_workspace_bytes(None, 1, 1024, ctypes.byref(n)) == -1
@@ -40,7 +40,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.EncLayerDesc) == 88
     assert ctypes.sizeof(_lib.EncoderDesc) == 24 + 8 * 88 + 5 * 8 + 8 + 8
     assert ctypes.sizeof(_lib.EncoderIO) == 8 + 16 + 5 * 8 + 3 * 64 + 16 + 2 * 64
-    assert ctypes.sizeof(_lib.DecoderDesc) == 16 + 2 * 96 + 16 + 2 * 48 + 96
+    assert ctypes.sizeof(_lib.DecoderDesc) == 16 + 2 * 96 + 16 + 2 * 48 + 96 + 2 * 96 + 4 * 8
 
 
 def test_state_dict_keys_match_reference_checkpoint():
