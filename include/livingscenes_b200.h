@@ -307,6 +307,32 @@ LS_API int ls_sdf_backward(const ls_decoder_desc* desc, const float* query, cons
                     float* grad_query, float* grad_z_so3, float* grad_z_inv, float* grad_s, float* grad_t,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Mesh extraction: MISE octree refinement + marching cubes
+ *   mesh_extractor2.py:88-131,158-181; utils/libmise/mise.pyx; utils/libmcubes
+ * R = resolution0 << depth.  Caller-owned device arrays: state u8 [(R+1)^3] (0 absent, 1 unknown, 2 known),
+ * val f32 [(R+1)^3], level u8 [R^3], pos / neg u8 [R^3].  One refinement round:
+ *   ls_mise_collect (query list + count) -> ls_mise_points (canonical coordinates box*(p/R-0.5)) -> SDF query ->
+ *   ls_mise_update (values * value_scale stored, active leaf voxels subdivided, new lattice points created)
+ * until the count is 0; ls_mise_to_dense completes the (R+1)^3 grid like MISE.to_dense.
+ * ------------------------------------------------------------------------------------------ */
+LS_API int ls_mise_init(int32_t resolution0, int32_t depth, uint8_t* state, uint8_t* level, void* stream);
+LS_API int ls_mise_collect(const uint8_t* state, int32_t R, int32_t* list, int32_t capacity, int32_t* count, void* stream);
+LS_API int ls_mise_points(const int32_t* list, int32_t n, int32_t R, float box_size, float* query, void* stream);
+LS_API int ls_mise_update(const int32_t* list, const float* values, int32_t n, float value_scale, int32_t R,
+                   int32_t depth, float threshold, float* val, uint8_t* state, uint8_t* level, uint8_t* pos,
+                   uint8_t* neg, void* stream);
+LS_API int ls_mise_to_dense(const uint8_t* state, const float* val, int32_t R, float* dense, void* stream);
+/* Marching cubes on grid [n,n,n] padded with -1e6 (mesh_extractor2.py:172), corner test value <= iso, vertices in the
+ * extractor's final frame box*((c-1)/(n-1)-0.5).  ls_mcubes_count writes {#vertices, #triangles} to the device ints
+ * n_out[2]; after reading them the caller allocates vertices [V,3] fp32 / faces [F,3] int64 and calls ls_mcubes_emit
+ * with the same workspace. */
+LS_API int ls_mcubes_workspace_bytes(int32_t n, size_t* bytes);
+LS_API int ls_mcubes_count(const float* grid, int32_t n, float iso, void* workspace, size_t workspace_bytes,
+                    int32_t* n_out, void* stream);
+LS_API int ls_mcubes_emit(const float* grid, int32_t n, float iso, float box_size, const void* workspace,
+                   float* vertices, int64_t* faces, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

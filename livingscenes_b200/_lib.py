@@ -114,6 +114,15 @@ _PROTOS = {
     "ls_sdf_backward_workspace_bytes": (C.c_int, [C.POINTER(DecoderDesc), C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "ls_sdf_backward": (C.c_int, [C.POINTER(DecoderDesc)] + [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 7 +
                         [C.c_size_t, C.c_void_p]),
+    "ls_mise_init": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_mise_collect": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ls_mise_points": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    "ls_mise_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ls_mise_to_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ls_mcubes_workspace_bytes": (C.c_int, [C.c_int32, C.POINTER(C.c_size_t)]),
+    "ls_mcubes_count": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "ls_mcubes_emit": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ls_sdf_decode": (C.c_int, [C.POINTER(DecoderDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
 }

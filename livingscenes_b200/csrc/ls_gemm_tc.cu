@@ -30,7 +30,7 @@
 //                          the accumulator;
 //               warps 0-3  epilogue: tcgen05.ld of accumulator buffer i while the MMAs of tile i+1 fill buffer
 //                          i^1 (2 x 128 TMEM columns).
-//               Rings: 4 operand stages (32 KB each), 4 raw stages (8 KB each); no __syncthreads in the tile loop.
+//               Rings: 3 operand stages (32 KB each), 6 raw stages (8 KB each); no __syncthreads in the tile loop.
 #include <cuda.h>
 
 #include <atomic>
@@ -313,12 +313,17 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
 // =====================================================================================================
 // k_gemm_tc2: persistent warp-specialised variant (see the header comment)
 // =====================================================================================================
-constexpr int G2_S = 4, G2_RS = 4;                 // operand stages, raw activation stages
+constexpr int G2_S = 3, G2_RS = 6;                 // operand stages, raw activation stages
 // The raw -> hi/lo transform of one k-block is a ~600-cycle dependent chain per warp (LDS, split, 8 STS, proxy fence,
 // arrive) against 384 cycles of MMA work per k-block: with one transform group the round-2 profile showed the epilogue
 // and the MMA warp waiting on it (profiles/r02/ncu_gemm_tc2_v2a.txt).  G2_XF_GROUPS groups of 4 warps take the k-blocks
 // round robin, so several k-blocks are transformed concurrently.
+// INVARIANT: a ring stage is always served by the same group (G2_XF_GROUPS divides G2_S and G2_RS).  An mbarrier
+// parity wait is only meaningful for a waiter that observes every phase of the barrier in order: a group that skipped a
+// use of a stage could arrive two phases early, see the parity of the phase before last as "complete" and read a stage
+// the TMA unit has not filled yet (measured: wrong tiles at N = 2048 with 3 groups over 4 stages).
 constexpr int G2_XF_GROUPS = 3;
+static_assert(G2_S % G2_XF_GROUPS == 0 && G2_RS % G2_XF_GROUPS == 0, "a ring stage must always be served by the same transform group");
 constexpr int G2_XF_WARP0 = 4, G2_PROD_WARP = 4 + 4 * G2_XF_GROUPS, G2_MMA_WARP = G2_PROD_WARP + 1;
 constexpr int G2_THREADS = 32 * (G2_MMA_WARP + 1);  // warps 0-3 epilogue, 4.. transform groups, producer, MMA
 constexpr int G2_TMEM_COLS = 2 * TN;                // two accumulator buffers

@@ -185,3 +185,61 @@ def test_fps_restatement_start_index_and_coverage():
         d = torch.cdist(pts, sub).min(-1).values.max(-1).values  # covering radius per cloud
         radius.append(d)
     assert bool((radius[1] <= radius[0]).all()) and bool((radius[2] <= radius[1]).all())
+
+
+# ------------------------------------------------------------------------------------------ MISE / marching cubes oracle
+def _field(kind):
+    if kind == "sphere":
+        return lambda p: 0.31 - np.linalg.norm(p - np.array([0.03, -0.02, 0.05]), axis=1)
+    if kind == "torus":
+        return lambda p: 0.09 - np.hypot(np.hypot(p[:, 0], p[:, 1]) - 0.28, p[:, 2])
+    rng = np.random.RandomState(3)
+    c = rng.uniform(-0.35, 0.35, (6, 3))
+    return lambda p: (np.exp(-((p[:, None, :] - c[None]) ** 2).sum(-1) / 0.02).sum(1) - 0.6).astype(np.float32).astype(np.float64)
+
+
+@pytest.mark.parametrize("kind,res0,depth", [("sphere", 8, 2), ("torus", 16, 2), ("blobs", 8, 3), ("sphere", 4, 0)])
+def test_mise_restatement_matches_reference_libmise(kind, res0, depth):
+    """oracle/mise_np.py against the reference's own compiled libmise (oracle/_ref): same query sets at every
+    refinement round and the same completed grid."""
+    from oracle import build_ref
+    from oracle.mise_np import MiseNP
+
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference; __graft_entry__.build() builds it)")
+    MISE, _ = ref
+    f = _field(kind)
+    a, b = MISE(res0, depth, 0.0), MiseNP(res0, depth, 0.0)
+    rounds = 0
+    while True:
+        pa, pb = a.query(), b.query()
+        assert pa.shape == pb.shape, (rounds, pa.shape, pb.shape)
+        if pa.shape[0] == 0:
+            break
+        key = lambda p: p[np.lexsort((p[:, 2], p[:, 1], p[:, 0]))]
+        assert np.array_equal(key(pa), key(pb)), rounds
+        va = f(1.1 * (pa / a.resolution - 0.5))
+        vb = f(1.1 * (pb / b.resolution - 0.5))
+        a.update(pa, va.astype(np.float64))
+        b.update(pb, vb)
+        rounds += 1
+    assert rounds >= 1
+    assert np.array_equal(a.to_dense(), b.to_dense())
+
+
+def test_mc_vertex_rule_matches_reference_libmcubes():
+    from oracle import build_ref
+    from oracle.mise_np import mc_vertices
+
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    _, mcubes = ref
+    g = np.mgrid[0:24, 0:24, 0:24].reshape(3, -1).T / 23.0 - 0.5
+    vol = np.pad(_field("blobs")(g * 1.1).reshape(24, 24, 24), 1, "constant", constant_values=-1e6)
+    v, f = mcubes(vol, 0.0)
+    mine = mc_vertices(vol, 0.0)
+    theirs = np.unique(v, axis=0)
+    assert mine.shape == theirs.shape and np.abs(mine - theirs[np.lexsort((theirs[:, 2], theirs[:, 1], theirs[:, 0]))]).max() < 1e-9
+    assert f.shape[0] > 100
