@@ -332,6 +332,87 @@ def oracle_sample_check(ls, model, sd, x_batch, n_set, n_take=4):
             "R_max_abs_err": float((out["R"].cpu() - Rk).abs().max())}
 
 
+def sdf_section(model, sd, dev, with_cpu=True, n_inst=64, M=100_000, timed=3):
+    """BASELINE config[4] / SURVEY C5: SDF decoder reconstruction query, 64 instances x 100 000 query points on one GPU.
+    Codes come from encoding 64 synthetic instances; queries are uniform in the 1.1-padded unit cube of every
+    instance's canonical frame (mesh_extractor2.py:100).  Device-resident timing (CUDA events) and an end-to-end leg
+    from pinned host memory (H2D of the queries, D2H of the SDF values inside the timed region)."""
+    from livingscenes_b200 import synthetic as S
+
+    x = S.synth_parts(n_inst, N_POINTS, 555).to(dev)
+    codes = model.encode(x)
+    q_host = S.sdf_queries(codes["s"].cpu(), codes["t"].cpu(), M, 1239).pin_memory()
+    q = q_host.to(dev)
+    fn = lambda qq: model.decoder(qq, None, codes, return_sdf=True)
+    for _ in range(2):
+        out = fn(q)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(timed):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(q)
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    h_out = torch.empty(n_inst, M).pin_memory()
+    e2e = []
+    for _ in range(timed):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        h_out.copy_(fn(q_host.to(dev, non_blocking=True)), non_blocking=True)
+        b.record()
+        b.synchronize()
+        e2e.append(a.elapsed_time(b))
+    t_ms, e_ms = statistics.median(ms), statistics.median(e2e)
+    _, _, _, tf32_peak, tf32_src = measured_peaks()
+    macs = 257 * 768 + 2 * 768 * 768 + 768 * 255 + 512 * 768 + 3 * 768 * 768 + 768   # per point after the layer-0/4 collapse
+    issued = 3 * 2 * macs * n_inst * M / (t_ms * 1e-3) / 1e12
+    # self-check on a sample against the CPU oracle
+    chk = None
+    cpu = None
+    if with_cpu:
+        from oracle import restatement as R
+
+        cc = {k: v[:2].cpu() for k, v in codes.items()}
+        qs = q_host[:2, :20000]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ref = R.sdf_decode(sd, qs, cc)
+        dt = time.perf_counter() - t0
+        chk = float((out[:2, :20000].cpu() - ref).abs().max())
+        assert chk < 1e-4, f"SDF values differ from the oracle: {chk}"
+        cpu = {"value": 40000 / dt, "unit": "query points/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"2 instances x 20 000 query points through oracle.restatement.sdf_decode ({dt:.1f} s)"}
+    return {"workload": f"BASELINE config[4]: SDF decoder query, {n_inst} instances x {M} points, 1 GPU", "metric": "query points/sec",
+            "value": n_inst * M / (t_ms * 1e-3), "unit": "query points/s", "ms": t_ms,
+            "e2e": {"value": n_inst * M / (e_ms * 1e-3), "unit": "query points/s", "ms": e_ms,
+                    "h2d_bytes": q_host.numel() * 4, "d2h_bytes": h_out.numel() * 4},
+            "roofline": {"bound": "tensor", "kernel": "k_gemm_tc2 (persistent tcgen05 3xTF32): the 8 hidden layers of the DeepSDF MLP",
+                         "achieved": issued, "peak": tf32_peak, "unit": "TFLOP/s", "frac": issued / tf32_peak,
+                         "peak_source": tf32_src, "flops": "executed: 3 TF32 MMA passes x 2 x 3.35 M MAC per point (SURVEY.md 7.1 fact 4)",
+                         "fp32_equivalent_TFLOPs": issued / 3},
+            "max_abs_err_vs_oracle_sample": chk, "cpu_baseline": cpu}
+
+
+def run_sdf(args):
+    import livingscenes_b200 as ls
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sd, wdesc = load_state_dict()
+    model = ls.Shape_Prior.from_state_dict(sd).to(dev).eval()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    sec = sdf_section(model, sd, dev, with_cpu=not args.no_cpu_baseline, timed=max(3, min(args.steps, 10)))
+    sec.update({"n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": f"synthetic ({wdesc})", "clocks": sampler.stop(),
+                "config": {"workload": sec.pop("workload")}, "vs_baseline": None, "scaling": "weak"})
+    print(json.dumps(sec))
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -640,6 +721,10 @@ def run_b200(args):
         gpu_eager = None
         if world == 1 and not args.no_gpu_eager:
             gpu_eager = gpu_eager_leg(sd, dev_sets[0], sizes)
+        sdf_c5 = None
+        if world == 1 and not args.no_sdf:
+            torch.cuda.empty_cache()
+            sdf_c5 = sdf_section(model, sd, dev, with_cpu=not args.no_cpu_baseline)
         line = {
             "metric": "instances/sec (N=1024 pts) encode+match+pose", "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -677,6 +762,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "gpu_eager_baseline": gpu_eager,
             "strong_c4": c4,
+            "sdf_c5": sdf_c5,
             "stages_ms": stages,
             "eager_ms_per_step": eager_ms / args.steps,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
@@ -709,9 +795,14 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline leg")
     ap.add_argument("--no-c4", action="store_true", help="skip the strong-scaling config[3] section")
+    ap.add_argument("--no-sdf", action="store_true", help="skip the SDF decoder config[4] section")
+    ap.add_argument("--workload", default="encode", choices=["encode", "sdf"],
+                    help="encode: the headline encode+match+pose step; sdf: BASELINE config[4] alone (query points/s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sdf":
+        run_sdf(args)
     else:
         run_b200(args)
 

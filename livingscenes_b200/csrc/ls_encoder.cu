@@ -124,6 +124,11 @@ long long g_wave_bytes = [] {
     const char* e = getenv("LS_WAVE_MB");
     return (long long)(e ? atof(e) : 0.0) * (1LL << 20);
 }();
+// small source sets (Ns <= 128): shared-memory tiled kernel (default) or the round-1 warp-per-query kernel (LS_KNN_SMALL_TILED=0)
+bool g_knn_small_tiled = [] {
+    const char* e = getenv("LS_KNN_SMALL_TILED");
+    return !(e && atoi(e) == 0);
+}();
 bool g_use_knn_tc = true;      // tensor-core candidate filter for the larger source sets
 float g_knn_tc_kappa_scale = 1.f;
 
@@ -495,8 +500,11 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         // ---- kNN graph (whole batch, caller's stream)
         if (ea.idx_in == nullptr && Ns <= SMALL_NS && !(g_use_knn_tc && Ns >= small_tc_min())) {
             ProfScope ps(4, i, st);
-            dim3 gs((Nd + 7) / 8, B);
-            k_knn_small<<<gs, 256, 0, st>>>(src_f, dst_f, Ci * 3, Ns, Nd, p.small_idx, nullptr);
+            if (g_knn_small_tiled) {
+                k_knn_small_tiled<<<dim3((Nd + 31) / 32, B), 256, 0, st>>>(src_f, dst_f, Ci * 3, Ns, Nd, p.small_idx, nullptr);
+            } else {
+                k_knn_small<<<dim3((Nd + 7) / 8, B), 256, 0, st>>>(src_f, dst_f, Ci * 3, Ns, Nd, p.small_idx, nullptr);
+            }
             LS_CHECK_LAUNCH("k_knn_small");
             ea.idx_in = p.small_idx;
         }
@@ -633,8 +641,29 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             ProfScope ps(5, i, st);
             k_row_mean<<<dim3((Co * 3 + 7) / 8, B), 256, 0, st>>>(p.pooled, Co * 3, Nd, p.gmean);
             LS_CHECK_LAUNCH("k_row_mean");
-            k_bias_gemv<<<dim3((2 * Co + 7) / 8, B), 256, (size_t)Co * 3 * sizeof(float), st>>>(p.gmean, Co, L.w_g2, p.bias);
-            LS_CHECK_LAUNCH("k_bias_gemv");
+            if (Co >= 128) {
+                // bias[b][r][a] = sum_c Wg2[r][c] g[b][c][a] as ONE batched FP32 GEMM over all instances (R = 2 Co rows,
+                // 3 B columns): the per-(instance, 8 rows) gemv CTAs re-read the 2 MB weight matrix 256 times (0.12 ms at
+                // layer 6 for 0.8 GFLOP)
+                GemmArgs gb{};
+                gb.W = L.w_g2;
+                gb.R = 2 * Co;
+                gb.K = Co;
+                gb.ldw = Co;
+                gb.B = B;
+                gb.X = p.gmean;
+                gb.n_per_b = 3;
+                gb.x_sb = (long long)Co * 3;
+                gb.x_sk = 3;
+                gb.out = p.bias;
+                gb.o_sb = 2LL * Co * 3;
+                gb.o_sr = 3;
+                rc = launch_gemm_simt(gb, st);
+                if (rc != LS_OK) return rc;
+            } else {
+                k_bias_gemv<<<dim3((2 * Co + 7) / 8, B), 256, (size_t)Co * 3 * sizeof(float), st>>>(p.gmean, Co, L.w_g2, p.bias);
+                LS_CHECK_LAUNCH("k_bias_gemv");
+            }
             GemmArgs g{};
             g.W = L.w_g1;
             g.Wtc = L.w_g1_tc;
@@ -784,8 +813,10 @@ int ls_knn(const float* query, const float* source, int32_t B, int32_t D, int32_
     ea.idx_out = idx;
     ea.dist_out = dist2;
     if (Ns <= SMALL_NS) {
-        dim3 gs((Nq + 7) / 8, B);
-        k_knn_small<<<gs, 256, 0, static_cast<cudaStream_t>(stream)>>>(source, query, D, Ns, Nq, idx, dist2);
+        if (g_knn_small_tiled)
+            k_knn_small_tiled<<<dim3((Nq + 31) / 32, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(source, query, D, Ns, Nq, idx, dist2);
+        else
+            k_knn_small<<<dim3((Nq + 7) / 8, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(source, query, D, Ns, Nq, idx, dist2);
         LS_CHECK_LAUNCH("k_knn_small");
         return LS_OK;
     }

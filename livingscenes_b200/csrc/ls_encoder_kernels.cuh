@@ -1035,6 +1035,87 @@ __global__ void __launch_bounds__(256) k_knn_small(const float* __restrict__ src
     }
 }
 
+// Tiled variant (default): one CTA = 32 queries of one instance x all Ns <= 128 sources.  The [dims][points] tiles of
+// both operands are staged in shared memory (coalesced global loads, every element read once per CTA instead of once
+// per warp), warp w owns a group of `spw` sources and lane = query, so a source value is one broadcast LDS.128 per 4
+// sources and the distance is the same sequential fp32 chain fmaf(q - s, q - s, acc) over d = 0..D-1 as everywhere
+// else (bit-identical keys).  The selection reuses the warp bitonic network on the [32][Ns] distances.
+// Round 2: layers 5-6 (D = 384 / 768, 32 queries per instance) took 0.23 + 0.36 ms with the warp-per-query kernel
+// above, latency-bound on 2 dependent global loads per dimension.
+constexpr int KS_DK = 32;
+__global__ void __launch_bounds__(256) k_knn_small_tiled(const float* __restrict__ src_f, const float* __restrict__ dst_f,
+                                                         int D, int Ns, int Nd, int64_t* __restrict__ idx_out,
+                                                         float* __restrict__ dist_out) {
+    __shared__ __align__(16) float s_src[KS_DK][128];
+    __shared__ float s_dst[KS_DK][33];
+    __shared__ float s_dist[32][129];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int b = blockIdx.y, q0 = blockIdx.x * 32;
+    const float* srcb = src_f + (size_t)b * D * Ns;
+    const float* dstb = dst_f + (size_t)b * D * Nd;
+    const int spw = (((Ns + 7) >> 3) + 3) & ~3;  // sources per warp, multiple of 4, <= 16
+    const int s0 = w * spw;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += KS_DK) {
+        for (int i = t; i < KS_DK * 128; i += 256) {
+            const int dd = i >> 7, sidx = i & 127;
+            s_src[dd][sidx] = (d0 + dd < D && sidx < Ns) ? __ldg(srcb + (size_t)(d0 + dd) * Ns + sidx) : 0.f;
+        }
+        for (int i = t; i < KS_DK * 32; i += 256) {
+            const int dd = i >> 5, qq = i & 31;
+            s_dst[dd][qq] = (d0 + dd < D && q0 + qq < Nd) ? __ldg(dstb + (size_t)(d0 + dd) * Nd + q0 + qq) : 0.f;
+        }
+        __syncthreads();
+        // dims past D are staged as 0 for both operands: fmaf(0, 0, acc) == acc exactly
+#pragma unroll 2
+        for (int dd = 0; dd < KS_DK; ++dd) {
+            const float qv = s_dst[dd][lane];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                if (j4 * 4 < spw && s0 + j4 * 4 < 128) {  // warp-uniform
+                    const float4 sv = *reinterpret_cast<const float4*>(&s_src[dd][s0 + j4 * 4]);
+                    float df = qv - sv.x;
+                    acc[j4 * 4 + 0] = fmaf(df, df, acc[j4 * 4 + 0]);
+                    df = qv - sv.y;
+                    acc[j4 * 4 + 1] = fmaf(df, df, acc[j4 * 4 + 1]);
+                    df = qv - sv.z;
+                    acc[j4 * 4 + 2] = fmaf(df, df, acc[j4 * 4 + 2]);
+                    df = qv - sv.w;
+                    acc[j4 * 4 + 3] = fmaf(df, df, acc[j4 * 4 + 3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j < spw && s0 + j < Ns) s_dist[lane][s0 + j] = acc[j];
+    __syncthreads();
+    // selection: warp w ranks queries 4w .. 4w+3
+    for (int qq = w * 4; qq < w * 4 + 4; ++qq) {
+        const int n = q0 + qq;
+        if (n >= Nd) break;  // warp-uniform
+        u64 lk = lane < Ns ? make_key(s_dist[qq][lane], lane) : KEY_MAX;
+        bitonic_sort32(lk, lane, false);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            if (32 * j < Ns) {  // warp-uniform
+                const int sidx = lane + 32 * j;
+                u64 bk = sidx < Ns ? make_key(s_dist[qq][sidx], sidx) : KEY_MAX;
+                bitonic_sort32(bk, lane, true);
+                lk = bk < lk ? bk : lk;
+                bitonic_merge32(lk, lane);
+            }
+        }
+        if (lane < LS_KNN_K) {
+            idx_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = min(key_idx(lk) & 0x7fffffff, Ns - 1);
+            if (dist_out) dist_out[((size_t)b * Nd + n) * LS_KNN_K + lane] = key_dist(lk);
+        }
+    }
+}
+
 // ---- exact re-rank of the tensor-core candidates.  The squared distance is the reference's direct form
 //      sum_d (q_d - s_d)^2 accumulated with one fp32 FMA per dimension in ascending d -- the same operation
 //      sequence as the brute-force tiles above, so both paths produce bit-identical keys.

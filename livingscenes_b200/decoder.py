@@ -151,7 +151,13 @@ class DeepSDF_Decoder(nn.Module):
         _lib.require_cuda(query, "query")
         dev = query.device
         q = query.detach().float().contiguous()
-        B, M, _ = q.shape
+        B, M0, _ = q.shape
+        if M0 % 4:
+            # the tcgen05 GEMMs need 16-byte aligned column groups; an odd point count would send the whole call through
+            # the FP32 SIMT GEMM, whose results differ from the 3xTF32 ones in the last bits.  Padding keeps the value of a
+            # point independent of how many points share its call (the MISE loop queries ragged lists).
+            q = torch.cat([q, q[:, -1:].expand(B, 4 - M0 % 4, 3)], 1).contiguous()
+        M = q.shape[1]
         z_so3 = code["z_so3"].detach().float().contiguous()
         z_inv = code["z_inv"].detach().float().contiguous()
         s = code["s"].detach().float().reshape(B).contiguous()
@@ -170,7 +176,7 @@ class DeepSDF_Decoder(nn.Module):
             _lib.check(rc, "ls_sdf_decode")
             _lib.launch_count += 1
             ws.record_stream(torch.cuda.current_stream(dev))
-        return sdf
+        return sdf if M == M0 else sdf[:, :M0].contiguous()
 
     BWD_MAX_COLS = 131072
 
