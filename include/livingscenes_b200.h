@@ -161,6 +161,11 @@ LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 pa
 /* 2 (default): persistent warp-specialised tcgen05 GEMM (bulk-TMA fed, double-buffered TMEM); 1: the round-1
  * one-CTA-per-tile kernel (kept for A/B measurements).  Process-global, like the other ls_set_* switches. */
 LS_API int ls_set_gemm_variant(int32_t variant);
+/* FPS squared distance: 0 (default) dx*dx + dy*dy + dz*dz with every product and sum rounded to fp32 (pytorch3d's
+ * CPU path, the oracle and the committed fixtures); 1: fma(dz,dz,fma(dy,dy,dx*dx)), what nvcc's default contraction
+ * makes of pytorch3d's CUDA kernel `dist2 += diff*diff`.  They differ in the last bit; only a near-tie arg-max can
+ * tell them apart.  Which one the reference's pytorch3d 0.7.4 binary runs is unpinned (not vendored). */
+LS_API int ls_set_fps_fma(int32_t on);
 /* Table bytes per wave of the per-layer {point-level table GEMMs -> EdgeConv} schedule (default 0 = off, env LS_WAVE_MB; measured slower on B200, see profiles/r02):
  * a layer's batch is processed in waves of that many bytes of gather tables, two table slots alternating, so that
  * the tables are consumed out of L2 instead of HBM.  0: one launch per layer for the whole batch.  Results do not

@@ -83,6 +83,7 @@ _PROTOS = {
     "ls_set_tensor_cores": (C.c_int, [C.c_int32]),
     "ls_set_gemm_variant": (C.c_int, [C.c_int32]),
     "ls_set_wave_bytes": (C.c_int, [C.c_int64]),
+    "ls_set_fps_fma": (C.c_int, [C.c_int32]),
     "ls_set_overlap": (C.c_int, [C.c_int32]),
     "ls_set_knn_tensor_cores": (C.c_int, [C.c_int32, C.c_float]),
     "ls_knn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -207,6 +208,11 @@ def set_gemm_variant(variant: int) -> None:
 def set_wave_bytes(nbytes: int) -> None:
     """Table bytes per wave of the {table GEMM -> EdgeConv} schedule (0: whole batch per launch, as in round 1)."""
     check(lib().ls_set_wave_bytes(int(nbytes)), "ls_set_wave_bytes")
+
+
+def set_fps_fma(on: bool) -> None:
+    """FPS squared distance FMA-contracted (pytorch3d's CUDA kernel under nvcc's default) instead of separately rounded."""
+    check(lib().ls_set_fps_fma(int(on)), "ls_set_fps_fma")
 
 
 def set_overlap(on: bool) -> None:

@@ -129,6 +129,7 @@ bool g_knn_small_tiled = [] {
     const char* e = getenv("LS_KNN_SMALL_TILED");
     return !(e && atoi(e) == 0);
 }();
+int g_fps_fma = 0;             // FPS squared distance: 0 = every product / sum rounded (oracle, fixtures), 1 = FMA-contracted
 bool g_use_knn_tc = true;      // tensor-core candidate filter for the larger source sets
 float g_knn_tc_kappa_scale = 1.f;
 
@@ -316,7 +317,8 @@ int launch_edge(int mode, const EdgeArgs& a, cudaStream_t st) {
     return LS_OK;
 }
 
-int launch_fps(const FpsArgs& a, int B, cudaStream_t st) {
+int launch_fps(FpsArgs a, int B, cudaStream_t st) {
+    a.fma = g_fps_fma;
     const int N = a.N;
     LS_REQUIRE(N >= 1 && N <= 8192, "fps: N must be in [1, 8192] (in-register running min distance)");
     for (int l = 0; l < a.n_levels; ++l) {
@@ -768,6 +770,10 @@ int ls_set_tensor_cores(int32_t on) {
     ls::g_use_tensor_cores = on != 0;
     return LS_OK;
 }
+int ls_set_fps_fma(int32_t on) {
+    ls::g_fps_fma = on != 0;
+    return LS_OK;
+}
 int ls_set_wave_bytes(int64_t bytes) {
     LS_REQUIRE(bytes >= 0, "wave bytes must be >= 0");
     ls::g_wave_bytes = bytes;
@@ -918,7 +924,7 @@ int ls_fps_ex(const float* xyz, int32_t B, int32_t N, int32_t n_out, const int64
         LS_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)B * N * sizeof(float4),
                    "fps: N > 8192 needs the scratch of ls_fps_workspace_bytes");
         LS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "fps: workspace must be 16-byte aligned");
-        k_fps_large<<<B, 1024, 0, st>>>(xyz, N, n_out, start_idx, static_cast<float4*>(workspace), idx, out_xyz);
+        k_fps_large<<<B, 1024, 0, st>>>(xyz, N, n_out, start_idx, static_cast<float4*>(workspace), idx, out_xyz, g_fps_fma);
         LS_CHECK_LAUNCH("k_fps_large");
         return LS_OK;
     }
@@ -941,7 +947,7 @@ int ls_fps_masked(const float* xyz, const uint8_t* mask, int32_t B, int32_t Nmax
                "fps_masked: workspace must hold B * Nmax float4");
     LS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "fps_masked: workspace must be 16-byte aligned");
     k_fps_masked<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(xyz, mask, Nmax, n_out, start_idx,
-                                                                     static_cast<float4*>(workspace), n_valid, idx, out_xyz);
+                                                                     static_cast<float4*>(workspace), n_valid, idx, out_xyz, g_fps_fma);
     LS_CHECK_LAUNCH("k_fps_masked");
     return LS_OK;
 }

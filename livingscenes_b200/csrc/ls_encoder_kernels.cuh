@@ -151,7 +151,18 @@ struct FpsArgs {
     const int64_t* force[FPS_MAX_LEVELS];  // optional forced selections (teacher forcing)
     float* out_xyz;                      // optional [B][3][n_out[last]]
     const int64_t* start;                // optional [B] first selected index of level 0 (default 0)
+    int fma;                             // squared distance as fma(dz,dz,fma(dy,dy,dx*dx)) instead of 3 mul + 2 add
 };
+
+// Squared distance of the FPS update.  pytorch3d's CUDA kernel accumulates `dist2 += diff * diff` over the 3
+// coordinates, which nvcc contracts to FMAs by default; its CPU implementation and torch expressions round every
+// product and sum.  The two differ in the last bit, which can flip a near-tie arg-max.  Default: separately rounded
+// (what the oracle / fixtures use); ls_set_fps_fma(1) selects the contracted form.  pytorch3d is not vendored in the
+// reference tree, so which of the two its 0.7.4 binary really executes is unpinned.
+__device__ __forceinline__ float fps_dist(float dx, float dy, float dz, int fma) {
+    return fma ? fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)))
+               : __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
 
 template <int PPT>
 __global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
 #pragma unroll
                 for (int p = 0; p < PPT; ++p) {
                     float dx = px[p] - lx, dy = py[p] - ly, dz = pz[p] - lz;
-                    float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                    float d = fps_dist(dx, dy, dz, a.fma);
                     float m = fminf(md[p], d);
                     if (md[p] >= 0.f) md[p] = m;
                     if (md[p] > bv) {  // strict: lowest index within the thread wins
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(1024) k_fps(const FpsArgs a) {
 // as k_fps.  With a mask the valid points are first compacted (stable order, like pc.T[mask]) into the scratch, so
 // a whole batch of ragged instances is sampled by ONE launch; indices then refer to the compacted list.
 __device__ __forceinline__ void fps_scratch_loop(float4* __restrict__ sb, int N, int n_out, int last, int b,
-                                                 int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+                                                 int64_t* __restrict__ sel64, float* __restrict__ out_xyz, int fma) {
     __shared__ float wb_v[2][32];
     __shared__ int wb_i[2][32];
     const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
@@ -296,7 +307,7 @@ __device__ __forceinline__ void fps_scratch_loop(float4* __restrict__ sb, int N,
         for (int i = t; i < N; i += T) {
             const float4 p = sb[i];
             const float dx = p.x - lx, dy = p.y - ly, dz = p.z - lz;
-            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const float d = fps_dist(dx, dy, dz, fma);
             const float m = fminf(p.w, d);
             sb[i].w = m;
             if (m > bv) {  // strict: lowest index within the thread wins
@@ -337,13 +348,13 @@ __device__ __forceinline__ void fps_scratch_loop(float4* __restrict__ sb, int N,
 
 __global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xyz, int N, int n_out,
                                                     const int64_t* __restrict__ start, float4* __restrict__ scr,
-                                                    int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+                                                    int64_t* __restrict__ sel64, float* __restrict__ out_xyz, int fma) {
     const int T = blockDim.x, b = blockIdx.x, t = threadIdx.x;
     const float* xb = xyz + (size_t)b * 3 * N;
     float4* sb = scr + (size_t)b * N;
     for (int i = t; i < N; i += T) sb[i] = make_float4(xb[i], xb[N + i], xb[2 * N + i], FLT_MAX);
     __syncthreads();
-    fps_scratch_loop(sb, N, n_out, start ? (int)start[b] : 0, b, sel64, out_xyz);
+    fps_scratch_loop(sb, N, n_out, start ? (int)start[b] : 0, b, sel64, out_xyz, fma);
 }
 
 // xyz [B][3][Nmax], mask [B][Nmax] (bytes, non-zero = valid).  n_valid[b] receives the number of valid points; an
@@ -351,7 +362,7 @@ __global__ void __launch_bounds__(1024) k_fps_large(const float* __restrict__ xy
 __global__ void __launch_bounds__(1024) k_fps_masked(const float* __restrict__ xyz, const unsigned char* __restrict__ mask,
                                                      int Nmax, int n_out, const int64_t* __restrict__ start,
                                                      float4* __restrict__ scr, int32_t* __restrict__ n_valid,
-                                                     int64_t* __restrict__ sel64, float* __restrict__ out_xyz) {
+                                                     int64_t* __restrict__ sel64, float* __restrict__ out_xyz, int fma) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int T = blockDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = T >> 5;
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(1024) k_fps_masked(const float* __restrict__ x
     if (N == 0) return;
     int first = start ? (int)start[b] : 0;
     first = min(max(first, 0), N - 1);
-    fps_scratch_loop(sb, N, n_out, first, b, sel64, out_xyz);
+    fps_scratch_loop(sb, N, n_out, first, b, sel64, out_xyz, fma);
 }
 
 // dst_f[b][r][j] = src_f[b][r][sel[b][j]]   (vec_dgcnn_atten.py:173; r runs over C*3 rows)

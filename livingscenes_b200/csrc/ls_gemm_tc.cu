@@ -22,15 +22,16 @@
 //   k_gemm_tc   (round 1) one CTA per tile, operands staged through registers, 2-stage ring, __syncthreads per
 //               k-block.  Kept as the A/B reference (ls_set_gemm_variant(1)).
 //   k_gemm_tc2  (default) persistent, warp-specialised: grid = #SMs, every CTA loops over output tiles;
-//               warp 16    producer: cp.async.bulk (TMA bulk, mbarrier complete_tx) of the 16 KB weight image of
-//                          the k-block and of the raw fp32 activation rows (512 B per k row and tile);
+//               warps 16-17 producers: cp.async.bulk (TMA bulk, mbarrier complete_tx) of the 16 KB weight image of
+//                          the k-block (warp 17) and ONE cp.async.bulk.tensor.3d per k-block for the raw fp32
+//                          activation tile [16 k][128 n] (warp 16, 9 stages of run-ahead);
 //               warps 4-15 transform (3 groups of 4, k-blocks round robin): raw [16 k][128 n] tile -> hi/lo TF32 split in the canonical K-major UMMA
 //                          image (the 4x4 register transpose of round 1, now smem -> smem);
-//               warp 17    one thread issues the tcgen05.mma's; tcgen05.commit frees the operand stage / publishes
+//               warp 18    one thread issues the tcgen05.mma's; tcgen05.commit frees the operand stage / publishes
 //                          the accumulator;
 //               warps 0-3  epilogue: tcgen05.ld of accumulator buffer i while the MMAs of tile i+1 fill buffer
 //                          i^1 (2 x 128 TMEM columns).
-//               Rings: 3 operand stages (32 KB each), 6 raw stages (8 KB each); no __syncthreads in the tile loop.
+//               Rings: 3 operand stages (32 KB each), 9 raw stages (8 KB each); no __syncthreads in the tile loop.
 #include <cuda.h>
 
 #include <atomic>
@@ -53,16 +54,19 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+    // instead of polling -- in the round-2 profile 40 % of the persistent kernel's issued instructions were the
+    // YIELD / TRYWAIT / BRA triplets of un-hinted polling loops, competing with the MMA-issuing thread for issue slots
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 
@@ -89,6 +93,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_n(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_gemm_tc(const GemmArgs a, const 
 // =====================================================================================================
 // k_gemm_tc2: persistent warp-specialised variant (see the header comment)
 // =====================================================================================================
-constexpr int G2_S = 3, G2_RS = 6;                 // operand stages, raw activation stages
+constexpr int G2_S = 3, G2_RS = 9;                 // operand stages, raw activation stages
 // The raw -> hi/lo transform of one k-block is a ~600-cycle dependent chain per warp (LDS, split, 8 STS, proxy fence,
 // arrive) against 384 cycles of MMA work per k-block: with one transform group the round-2 profile showed the epilogue
 // and the MMA warp waiting on it (profiles/r02/ncu_gemm_tc2_v2a.txt).  G2_XF_GROUPS groups of 4 warps take the k-blocks
@@ -324,8 +338,12 @@ constexpr int G2_S = 3, G2_RS = 6;                 // operand stages, raw activa
 // the TMA unit has not filled yet (measured: wrong tiles at N = 2048 with 3 groups over 4 stages).
 constexpr int G2_XF_GROUPS = 3;
 static_assert(G2_S % G2_XF_GROUPS == 0 && G2_RS % G2_XF_GROUPS == 0, "a ring stage must always be served by the same transform group");
-constexpr int G2_XF_WARP0 = 4, G2_PROD_WARP = 4 + 4 * G2_XF_GROUPS, G2_MMA_WARP = G2_PROD_WARP + 1;
-constexpr int G2_THREADS = 32 * (G2_MMA_WARP + 1);  // warps 0-3 epilogue, 4.. transform groups, producer, MMA
+// Two producer warps: the activation tiles come from HBM (first touch) and want a long run-ahead (9 raw stages =
+// ~3 500 cycles of MMA work), the weight images come from L2 and share the 3-stage operand ring with the transform
+// output.  With ONE producer loop the raw requests were throttled by the weight ring (3 k-blocks of run-ahead) and the
+// round-2 profile showed 27 % of the stall samples on the transform warps' wait for the raw tile.
+constexpr int G2_XF_WARP0 = 4, G2_PRODX_WARP = 4 + 4 * G2_XF_GROUPS, G2_PRODA_WARP = G2_PRODX_WARP + 1, G2_MMA_WARP = G2_PRODA_WARP + 1;
+constexpr int G2_THREADS = 32 * (G2_MMA_WARP + 1);  // warps 0-3 epilogue, 4.. transform groups, 2 producers, MMA
 constexpr int G2_TMEM_COLS = 2 * TN;                // two accumulator buffers
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -360,11 +378,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
-// tmap: activations as a 3-D tensor (n, k, instance) -- see make_act_map.  tile_per_b = column tiles per instance.
+// tmap: activations as a 3-D tensor (n, k, instance) -- see make_act_map.  tile_per_b = column tiles per instance;
+// tn = columns per tile (128, or 96 / 64 / 32 when an instance has fewer than 128 columns: UMMA N = tn).
 template <bool PM>
 __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, const float* __restrict__ wpk, int n_kb, int n_mt,
                                                             int n_tiles, const __grid_constant__ CUtensorMap tmap,
-                                                            int tile_per_b) {
+                                                            int tile_per_b, int tn) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     G2Shared& sh = *reinterpret_cast<G2Shared*>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -398,31 +417,36 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = sh.tmem_base;
 
-    if (w == G2_PROD_WARP) {
-        // ================================================================ producer: TMA (tensor + bulk) copies
-        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int mt = tile % n_mt;
-            const float* wtile = wpk + (size_t)mt * n_kb * (2 * A_STAGE_FLOATS);
-            const int ct = tile / n_mt, tb = ct / tile_per_b, tn0 = (ct - tb * tile_per_b) * TN;
-            for (int kb = 0; kb < n_kb; ++kb, ++it) {
-                // raw activation tile of this k-block: ONE tensor request (rows k >= K and columns past the end are
-                // zero-filled by the TMA unit; the transaction count is always the full box)
-                const int r = it % G2_RS;
-                if (it >= G2_RS) mbar_wait(&sh.raw_empty[r], ((it / G2_RS) - 1) & 1);
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&sh.raw_full[r], TKB * TN * 4);
+    if (w == G2_PRODX_WARP) {
+        // ================================================================ producer 1: activation tiles (TMA tensor requests)
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int ct = tile / n_mt, tb = ct / tile_per_b, tn0 = (ct - tb * tile_per_b) * tn;
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    // ONE tensor request per k-block (rows k >= K and columns past the end are zero-filled by the TMA
+                    // unit; the transaction count is always the full box)
+                    const int r = it % G2_RS;
+                    if (it >= G2_RS) mbar_wait(&sh.raw_empty[r], ((it / G2_RS) - 1) & 1);
+                    mbar_arrive_expect_tx(&sh.raw_full[r], (uint32_t)(TKB * tn * 4));
                     tma_load_3d(&sh.raw[r][0][0], &tmap, tn0, kb * TKB, tb, &sh.raw_full[r]);
                 }
-                // weight image of (m-tile, k-block): one contiguous 16 KB block (hi then lo)
-                const int s = it % G2_S;
-                if (it >= G2_S) mbar_wait(&sh.empty[s], ((it / G2_S) - 1) & 1);
-                if (lane == 0) {
+            }
+        }
+    } else if (w == G2_PRODA_WARP) {
+        // ================================================================ producer 2: weight images (TMA bulk copies)
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const float* wtile = wpk + (size_t)(tile % n_mt) * n_kb * (2 * A_STAGE_FLOATS);
+                for (int kb = 0; kb < n_kb; ++kb, ++it) {
+                    // (m-tile, k-block): one contiguous 16 KB block (hi then lo)
+                    const int s = it % G2_S;
+                    if (it >= G2_S) mbar_wait(&sh.empty[s], ((it / G2_S) - 1) & 1);
                     mbar_arrive_expect_tx(&sh.full_a[s], 2 * A_STAGE_FLOATS * 4);
                     bulk_g2s(&sh.a[s][0][0], wtile + (size_t)kb * (2 * A_STAGE_FLOATS), 2 * A_STAGE_FLOATS * 4, &sh.full_a[s]);
                 }
-                __syncwarp();
             }
         }
     } else if (w == G2_MMA_WARP) {
@@ -436,6 +460,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t d = tmem + (uint32_t)(acc * TN);
+                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tn >> 3) << 17) | ((TM >> 4) << 24);
+                const uint32_t b_lbo = (uint32_t)(tn / 8) * 128;  // k-core stride of the activation image
                 for (int kb = 0; kb < n_kb; ++kb, ++it) {
                     const int s = it % G2_S;
                     mbar_wait(&sh.full_a[s], (it / G2_S) & 1);
@@ -447,11 +473,11 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                     for (int ss = 0; ss < TKB / 8; ++ss) {
                         const uint64_t dah = make_desc(a_hi + ss * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
                         const uint64_t dal = make_desc(a_lo + ss * 2 * (TM / 8) * 128, (TM / 8) * 128, 128);
-                        const uint64_t dbh = make_desc(b_hi + ss * 2 * (TN / 8) * 128, (TN / 8) * 128, 128);
-                        const uint64_t dbl = make_desc(b_lo + ss * 2 * (TN / 8) * 128, (TN / 8) * 128, 128);
-                        umma_tf32(d, dal, dbh, (kb | ss) != 0);
-                        umma_tf32(d, dah, dbl, 1);
-                        umma_tf32(d, dah, dbh, 1);
+                        const uint64_t dbh = make_desc(b_hi + ss * 2 * b_lbo, b_lbo, 128);
+                        const uint64_t dbl = make_desc(b_lo + ss * 2 * b_lbo, b_lbo, 128);
+                        umma_tf32_n(d, dal, dbh, idesc, (kb | ss) != 0);
+                        umma_tf32_n(d, dah, dbl, idesc, 1);
+                        umma_tf32_n(d, dah, dbh, idesc, 1);
                     }
                     umma_commit(&sh.empty[s]);  // frees the operand stage when the MMAs have read it
                     if (kb == n_kb - 1) umma_commit(&sh.tmem_full[acc]);
@@ -468,37 +494,42 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                 if (it % G2_XF_GROUPS != grp) continue;
                 const int r = it % G2_RS;
                 mbar_wait(&sh.raw_full[r], (it / G2_RS) & 1);
-                float4 v[4];
+                const float* rawp = &sh.raw[r][0][0] + kc * 4 * tn;  // the TMA box is dense [16 k][tn columns] (row stride tn, not TN)
+                // Column n = i * 32 + lane: the four k values of a column ARE one 16-byte core-matrix row of the K-major
+                // image ([kcore][ngroup][8 n][4 k] = 4 * n floats into the k-core), so a thread reads 4 scalars (lanes =
+                // consecutive columns: conflict free) and writes one float4 per image (lanes = consecutive 16-byte rows:
+                // conflict free) -- no register transpose.  Out-of-range elements are TMA zero fill.
+                float4 c[4];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const int kl = kc * 4 + rr;
-                    v[rr] = *reinterpret_cast<const float4*>(&sh.raw[r][kl][lane * 4]);  // out-of-range elements are TMA zero fill
+                for (int i = 0; i < 4; ++i) {
+                    const int n = i * 32 + lane;
+                    if (n < tn) {
+                        c[i].x = rawp[n];
+                        c[i].y = rawp[tn + n];
+                        c[i].z = rawp[2 * tn + n];
+                        c[i].w = rawp[3 * tn + n];
+                    }
                 }
                 const int s = it % G2_S;
                 if (it >= G2_S) mbar_wait(&sh.empty[s], ((it / G2_S) - 1) & 1);
-                // the 4(k) x 4(n) block transposed: four 16-byte core-matrix rows of [kcore][ngroup][8 n][4 k],
-                // stored in a lane-rotated order (each quarter-warp hits 8 distinct 16-byte bank groups)
+                float* bh = &sh.b[s][0][kc * tn * 4];
+                float* bl = &sh.b[s][1][kc * tn * 4];
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    const int i = (s4 + (lane >> 1)) & 3;
-                    float4 c;
-                    c.x = i == 0 ? v[0].x : (i == 1 ? v[0].y : (i == 2 ? v[0].z : v[0].w));
-                    c.y = i == 0 ? v[1].x : (i == 1 ? v[1].y : (i == 2 ? v[1].z : v[1].w));
-                    c.z = i == 0 ? v[2].x : (i == 1 ? v[2].y : (i == 2 ? v[2].z : v[2].w));
-                    c.w = i == 0 ? v[3].x : (i == 1 ? v[3].y : (i == 2 ? v[3].z : v[3].w));
-                    float4 hi, lo;
-                    hi.x = __uint_as_float((__float_as_uint(c.x) + 0x1000u) & 0xffffe000u);
-                    hi.y = __uint_as_float((__float_as_uint(c.y) + 0x1000u) & 0xffffe000u);
-                    hi.z = __uint_as_float((__float_as_uint(c.z) + 0x1000u) & 0xffffe000u);
-                    hi.w = __uint_as_float((__float_as_uint(c.w) + 0x1000u) & 0xffffe000u);
-                    lo.x = c.x - hi.x;
-                    lo.y = c.y - hi.y;
-                    lo.z = c.z - hi.z;
-                    lo.w = c.w - hi.w;
-                    const int n = lane * 4 + i;
-                    const int off = ((kc * (TN / 8) + (n >> 3)) * 8 + (n & 7)) * 4;
-                    *reinterpret_cast<float4*>(&sh.b[s][0][off]) = hi;
-                    *reinterpret_cast<float4*>(&sh.b[s][1][off]) = lo;
+                for (int i = 0; i < 4; ++i) {
+                    const int n = i * 32 + lane;
+                    if (n < tn) {
+                        float4 hi, lo;
+                        hi.x = __uint_as_float((__float_as_uint(c[i].x) + 0x1000u) & 0xffffe000u);
+                        hi.y = __uint_as_float((__float_as_uint(c[i].y) + 0x1000u) & 0xffffe000u);
+                        hi.z = __uint_as_float((__float_as_uint(c[i].z) + 0x1000u) & 0xffffe000u);
+                        hi.w = __uint_as_float((__float_as_uint(c[i].w) + 0x1000u) & 0xffffe000u);
+                        lo.x = c[i].x - hi.x;
+                        lo.y = c[i].y - hi.y;
+                        lo.z = c[i].z - hi.z;
+                        lo.w = c[i].w - hi.w;
+                        *reinterpret_cast<float4*>(bh + n * 4) = hi;
+                        *reinterpret_cast<float4*>(bl + n * 4) = lo;
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
                 mbar_arrive(&sh.full_b[s]);
@@ -510,12 +541,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
         int lt = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const int acc = lt & 1, mt = tile % n_mt;
-            const long long c0 = (long long)(tile / n_mt) * TN;
+            const long long c0 = (long long)(tile / n_mt) * tn;
             asm volatile("bar.sync 1, 128;" ::: "memory");  // the previous tile's column tables are no longer read
             {
                 const long long j = c0 + t;
                 long long base = -1, boff = 0;
-                if (j < ncols) {
+                if (t < tn && j < ncols) {
                     const long long b = j / a.n_per_b;
                     const int n = (int)(j - b * a.n_per_b);
                     const int axis = a.npts > 0 ? n / a.npts : 0;
@@ -542,7 +573,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                 row_off = (long long)part * 3 * a.c_out + (r - part * a.c_out);
             }
 #pragma unroll 1
-            for (int cc = 0; cc < TN; cc += 32) {
+            for (int cc = 0; cc < tn; cc += 32) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * TN + cc);
                 asm volatile(
@@ -555,7 +586,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == TN - 32) {  // this thread's last read of the buffer: hand it back to the MMA warp
+                if (cc == tn - 32) {  // this thread's last read of the buffer: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&sh.tmem_empty[acc]);
                 }
@@ -569,39 +600,61 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                     }
                 } else {
                     // channel-major.  Bias + ReLU are applied while lane == row (the bias offset of a column is warp
-                    // uniform and rarely changes inside a chunk: one cached load instead of a dependent load per element),
-                    // then the warp's 32 x 32 block is transposed so that lanes store consecutive columns.
-                    float* tl = &sh.epi[w][0];
+                    // uniform and rarely changes inside a chunk: one cached load instead of a dependent load per element).
                     float bcache = 0.f;
                     long long last_bo = -1;
+                    float val[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float val = __uint_as_float(v[j]);
+                        val[j] = __uint_as_float(v[j]);
                         if (a.bias) {
                             const long long bo = sh.col_bias[cc + j];
                             if (bo != last_bo) {
                                 bcache = row_ok ? __ldg(a.bias + bo + (long long)r * a.bias_sr) : 0.f;
                                 last_bo = bo;
                             }
-                            val += bcache;
+                            val[j] += bcache;
                         }
-                        if (a.relu) val = fmaxf(val, 0.f);
-                        tl[lane * 33 + j] = val;
+                        if (a.relu) val[j] = fmaxf(val[j], 0.f);
                     }
-                    __syncwarp();
-                    const long long base = sh.col_base[cc + lane];
-                    if (base >= 0) {
-                        const int nrow = min(32, a.R - (r0 + w * 32));
-                        if (a.mask) {
-#pragma unroll 8
+                    const long long b0 = sh.col_base[cc], b31 = sh.col_base[cc + 31];
+                    // fast path (warp uniform): the chunk's 32 columns are valid, contiguous in the output and 16-byte
+                    // aligned -> every thread stores its own row as 8 float4 (no transpose through shared memory)
+                    const bool vec = b0 >= 0 && b31 - b0 == 31 && ((b0 | a.o_sr) & 3) == 0 &&
+                                     (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                                     (a.mask == nullptr || (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0);
+                    if (vec) {
+                        if (row_ok) {
+                            float4* o = reinterpret_cast<float4*>(a.out + b0 + (long long)r * a.o_sr);
+                            if (a.mask) {
+                                const float4* mk = reinterpret_cast<const float4*>(a.mask + b0 + (long long)r * a.o_sr);
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; ++j4) {
+                                    const float4 m4 = __ldg(mk + j4);
+                                    o[j4] = make_float4(m4.x > 0.f ? val[4 * j4] : 0.f, m4.y > 0.f ? val[4 * j4 + 1] : 0.f,
+                                                        m4.z > 0.f ? val[4 * j4 + 2] : 0.f, m4.w > 0.f ? val[4 * j4 + 3] : 0.f);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j4 = 0; j4 < 8; ++j4)
+                                    o[j4] = make_float4(val[4 * j4], val[4 * j4 + 1], val[4 * j4 + 2], val[4 * j4 + 3]);
+                            }
+                        }
+                    } else {
+                        // general path: transpose the warp's 32 x 32 block so that lanes store consecutive columns
+                        float* tl = &sh.epi[w][0];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tl[lane * 33 + j] = val[j];
+                        __syncwarp();
+                        const long long base = sh.col_base[cc + lane];
+                        if (base >= 0) {
+                            const int nrow = min(32, a.R - (r0 + w * 32));
                             for (int rr = 0; rr < nrow; ++rr) {
                                 const long long oo = base + (long long)(r0 + w * 32 + rr) * a.o_sr;
-                                a.out[oo] = __ldg(a.mask + oo) > 0.f ? tl[rr * 33 + lane] : 0.f;
+                                float x = tl[rr * 33 + lane];
+                                if (a.mask && !(__ldg(a.mask + oo) > 0.f)) x = 0.f;
+                                a.out[oo] = x;
                             }
-                        } else {
-#pragma unroll 8
-                            for (int rr = 0; rr < nrow; ++rr)
-                                a.out[base + (long long)(r0 + w * 32 + rr) * a.o_sr] = tl[rr * 33 + lane];
                         }
                     }
                     __syncwarp();
@@ -678,9 +731,15 @@ static int sm_count() {
 // The persistent kernel feeds its activations with ONE TMA tensor request per (tile, k-block): the activation tensor
 // X[b*x_sb + k*x_sk + n] must be expressible as a tiled tensor map whose 128-column boxes never straddle instances:
 // either the columns of consecutive instances are contiguous (x_sb == n_per_b: the SDF decoder's feature-major
-// layout -> one flat column axis), or n_per_b is a multiple of 128.  Other shapes (3 N = 96 columns per instance in
-// encoder layers 5-6 and the head) and launches with few tiles run the per-tile kernel, which is faster there.
-static bool gemm_v2_geometry(const GemmArgs& a) { return a.x_sb == a.n_per_b || a.n_per_b % TN == 0; }
+// layout -> one flat column axis), or n_per_b is a multiple of 128, or an instance has 32 / 64 / 96 columns (3 N = 96
+// in encoder layers 5-6 and the head: one tile per instance, UMMA N = 96).  Other shapes and launches with few tiles
+// run the per-tile kernel.
+static int gemm_v2_tile_cols(const GemmArgs& a) {
+    if (a.x_sb == a.n_per_b || a.n_per_b % TN == 0) return TN;
+    if (a.n_per_b < TN && a.n_per_b % 32 == 0) return a.n_per_b;  // 96 (3 x 32 points), 64, 32: one tile per instance, UMMA N = tile
+    return 0;
+}
+static bool gemm_v2_geometry(const GemmArgs& a) { return gemm_v2_tile_cols(a) != 0; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -698,7 +757,7 @@ static EncodeTiledFn encode_tiled_fn() {
     return reinterpret_cast<EncodeTiledFn>(f);
 }
 
-static int make_act_map(const GemmArgs& a, CUtensorMap* map, int* tile_per_b) {
+static int make_act_map(const GemmArgs& a, CUtensorMap* map, int* tile_per_b, int tn) {
     EncodeTiledFn enc = encode_tiled_fn();
     LS_REQUIRE(enc != nullptr, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
     const bool flat = a.x_sb == a.n_per_b;  // one contiguous column axis over all instances
@@ -706,7 +765,7 @@ static int make_act_map(const GemmArgs& a, CUtensorMap* map, int* tile_per_b) {
     const cuuint64_t nb = flat ? 1 : (cuuint64_t)a.B;
     const cuuint64_t dims[3] = {n0, (cuuint64_t)a.K, nb};
     const cuuint64_t strides[2] = {(cuuint64_t)a.x_sk * sizeof(float), (cuuint64_t)(flat ? n0 : a.x_sb) * sizeof(float)};
-    const cuuint32_t box[3] = {TN, TKB, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)tn, TKB, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.X), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -715,7 +774,7 @@ static int make_act_map(const GemmArgs& a, CUtensorMap* map, int* tile_per_b) {
         set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return LS_ERR_CUDA;
     }
-    *tile_per_b = (int)((n0 + TN - 1) / TN);
+    *tile_per_b = (int)((n0 + tn - 1) / tn);
     return LS_OK;
 }
 
@@ -730,8 +789,9 @@ int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
     const int n_kb = (a.K + TKB - 1) / TKB;
     // the dynamic shared-memory opt-in is per device: set it on every launch (cheap, legal under stream capture)
     // instead of caching a process-wide flag that a second device in the same process would never see
-    const long long tiles_all = ((ncols + TN - 1) / TN) * ((a.R + TM - 1) / TM);
-    if (g_gemm_variant == 1 || !gemm_v2_geometry(a) || tiles_all < 2LL * sm_count()) {
+    const int tn = gemm_v2_tile_cols(a);
+    const long long tiles_all = tn ? ((ncols + tn - 1) / tn) * ((a.R + TM - 1) / TM) : 0;
+    if (g_gemm_variant == 1 || tn == 0 || tiles_all < 2LL * sm_count()) {
         dim3 grid((unsigned)((ncols + TN - 1) / TN), (unsigned)((a.R + TM - 1) / TM));
         const size_t smem = sizeof(TcShared) + 128;
         if (a.point_major) {
@@ -744,22 +804,22 @@ int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
         LS_CHECK_LAUNCH("k_gemm_tc");
         return LS_OK;
     }
-    const long long n_ct = (ncols + TN - 1) / TN;
+    const long long n_ct = (ncols + tn - 1) / tn;
     const int n_mt = (a.R + TM - 1) / TM;
     LS_REQUIRE(n_ct * n_mt < (1LL << 31), "gemm_tc: too many tiles");
     const int n_tiles = (int)(n_ct * n_mt);
     CUtensorMap tmap;
     int tile_per_b = 0;
-    int rc = make_act_map(a, &tmap, &tile_per_b);
+    int rc = make_act_map(a, &tmap, &tile_per_b, tn);
     if (rc != LS_OK) return rc;
     const int grid = n_tiles < sm_count() ? n_tiles : sm_count();
     const size_t smem = sizeof(G2Shared) + 128;
     if (a.point_major) {
         LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gemm_tc2<true><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles, tmap, tile_per_b);
+        k_gemm_tc2<true><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles, tmap, tile_per_b, tn);
     } else {
         LS_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_gemm_tc2<false><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles, tmap, tile_per_b);
+        k_gemm_tc2<false><<<grid, G2_THREADS, smem, st>>>(a, packed, n_kb, n_mt, n_tiles, tmap, tile_per_b, tn);
     }
     LS_CHECK_LAUNCH("k_gemm_tc2");
     return LS_OK;

@@ -249,7 +249,8 @@ class VecDGCNN_att(nn.Module):
         return out
 
     def _workspace(self, desc, B: int, N: int, device) -> torch.Tensor:
-        key = (B, N, str(device))
+        # one workspace per (shape, device, stream): two forwards on different streams must not share scratch
+        key = (B, N, str(device), torch.cuda.current_stream(device).cuda_stream)
         ws = self._ws.get(key)
         if ws is None:
             nbytes = C.c_size_t(0)

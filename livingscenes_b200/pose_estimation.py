@@ -30,7 +30,10 @@ def kabsch_transformation_estimation(x1, x2, weights=None, normalize_w=True, eps
             normalize_w = False
         ind = torch.topk(w[0], best_k, largest=True).indices  # reference: indices of batch 0 for all
         w, x1, x2 = w[:, ind], x1[:, ind], x2[:, ind]
-    if w_threshold > 0 and w is not None:
+    if w_threshold > 0:
+        if w is None:  # the reference thresholds the normalised default weights 1 / (n + eps) too (pose_estimation.py:49-66)
+            w = torch.full(x1.shape[:2], 1.0 / (x1.shape[1] + eps) if normalize_w else 1.0, device=x1.device)
+            normalize_w = False
         w = torch.where(w < w_threshold, torch.zeros_like(w), w)
     x1, x2 = x1.contiguous(), x2.contiguous()
     b, n, _ = x1.shape

@@ -49,6 +49,10 @@ EXACT = True  # parity mode; bench's CPU-timing leg flips this to False
 # selected point would misrepresent it).
 ON_DEVICE = False
 FPS_IMPL = None
+# FPS distance arithmetic: False = every product and sum rounded to fp32 (canonical, the fixtures); True = emulates the
+# FMA-contracted form fma(dz,dz,fma(dy,dy,dx*dx)) of pytorch3d's CUDA kernel (products exact in float64, one rounding
+# per fma) -- the A/B partner of ls_set_fps_fma(1).
+FPS_FMA = False
 
 
 def _sqdist_f64(q: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
@@ -125,7 +129,12 @@ def sample_farthest_points(points, lengths=None, K: int = 50, random_start_point
         dx = px - px[ar, last][:, None]
         dy = py - py[ar, last][:, None]
         dz = pz - pz[ar, last][:, None]
-        d = dx * dx + dy * dy + dz * dz  # each op rounded to fp32, left to right
+        if FPS_FMA:
+            t1 = (dx * dx)                                                     # rounded product
+            t2 = (dy.double() * dy.double() + t1.double()).float()             # fma: exact product, one rounding
+            d = (dz.double() * dz.double() + t2.double()).float()
+        else:
+            d = dx * dx + dy * dy + dz * dz  # each op rounded to fp32, left to right
         min_d = torch.minimum(min_d, d)
         # argmax with lowest index on ties: torch.max over dim returns the first
         # maximal element on CPU; make it explicit to be safe.

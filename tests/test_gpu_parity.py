@@ -348,6 +348,29 @@ def test_fps_bit_exact(N, n_out, dev, oracle_R):
     assert torch.equal(sub.cpu(), rp.transpose(1, 2))
 
 
+@pytest.mark.parametrize("N,n_out", [(1024, 512), (5000, 1024), (20000, 300)])
+def test_fps_fma_switch_matches_the_contracted_oracle(N, n_out, dev, oracle_R):
+    """ls_set_fps_fma(1): the FMA-contracted distance (what nvcc makes of pytorch3d's CUDA kernel) against the shim's
+    emulation of it; both forms are bit-exact against their own oracle, and they do differ from each other somewhere."""
+    from livingscenes_b200 import _lib
+    from livingscenes_b200.ops import farthest_point_sample
+    from oracle import p3d_shim
+
+    x = oracle_R.synth_instances(2, N, 5 + N) * 37.3  # scaled: more mantissa bits in play
+    try:
+        _lib.set_fps_fma(True)
+        p3d_shim.FPS_FMA = True
+        idx, _ = farthest_point_sample(x.to(dev), n_out)
+        _, ridx = p3d_shim.sample_farthest_points(x.transpose(1, 2), K=n_out)
+        assert torch.equal(idx.cpu(), ridx)
+    finally:
+        _lib.set_fps_fma(False)
+        p3d_shim.FPS_FMA = False
+    idx0, _ = farthest_point_sample(x.to(dev), n_out)
+    _, ridx0 = p3d_shim.sample_farthest_points(x.transpose(1, 2), K=n_out)
+    assert torch.equal(idx0.cpu(), ridx0)
+
+
 def test_fps_ties_lowest_index(dev):
     from livingscenes_b200.ops import farthest_point_sample
 
@@ -379,7 +402,8 @@ def test_vn_linear_fp32_accurate(tensor_cores, B, Ci, Co, N, dev):
 
 
 @pytest.mark.parametrize("B,Ci,Co,N", [(3, 32, 64, 1024), (37, 64, 384, 512), (300, 128, 768, 128), (7, 256, 2048, 32),
-                                       (2, 512, 257, 32), (1, 257, 768, 1000), (4, 96, 40, 36), (256, 32, 128, 1024)])
+                                       (2, 512, 257, 32), (1, 257, 768, 1000), (4, 96, 40, 36), (256, 32, 128, 1024),
+                                       (300, 256, 512, 32), (260, 512, 1100, 32)])
 def test_gemm_persistent_equals_per_tile_kernel(B, Ci, Co, N, dev):
     """The persistent warp-specialised tcgen05 GEMM (bulk-TMA fed, double-buffered TMEM; many tiles per CTA at the
     larger sizes) issues the same MMAs in the same order as the round-1 one-tile-per-CTA kernel: bit-identical."""
