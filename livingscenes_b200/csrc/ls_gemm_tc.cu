@@ -342,8 +342,13 @@ static_assert(G2_S % G2_XF_GROUPS == 0 && G2_RS % G2_XF_GROUPS == 0, "a ring sta
 // ~3 500 cycles of MMA work), the weight images come from L2 and share the 3-stage operand ring with the transform
 // output.  With ONE producer loop the raw requests were throttled by the weight ring (3 k-blocks of run-ahead) and the
 // round-2 profile showed 27 % of the stall samples on the transform warps' wait for the raw tile.
-constexpr int G2_XF_WARP0 = 4, G2_PRODX_WARP = 4 + 4 * G2_XF_GROUPS, G2_PRODA_WARP = G2_PRODX_WARP + 1, G2_MMA_WARP = G2_PRODA_WARP + 1;
-constexpr int G2_THREADS = 32 * (G2_MMA_WARP + 1);  // warps 0-3 epilogue, 4.. transform groups, 2 producers, MMA
+// Two epilogue groups of 4 warps: group g drains accumulator buffer g (tiles g, g+2, ... of the CTA).  With ONE group the
+// round-2 profile showed its 4 warps (one per scheduler, nothing to hide their dependent-issue latency behind) busy 85 %
+// of the time at ~11 us per channel-major tile while the tensor pipe idled (7-36 % active, 54 % on the SDF decoder).
+constexpr int G2_EPI_GROUPS = 2;
+constexpr int G2_XF_WARP0 = 4 * G2_EPI_GROUPS, G2_PRODX_WARP = G2_XF_WARP0 + 4 * G2_XF_GROUPS, G2_PRODA_WARP = G2_PRODX_WARP + 1,
+              G2_MMA_WARP = G2_PRODA_WARP + 1;
+constexpr int G2_THREADS = 32 * (G2_MMA_WARP + 1);  // warps 0-7 epilogue, 8.. transform groups, 2 producers, MMA
 constexpr int G2_TMEM_COLS = 2 * TN;                // two accumulator buffers
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -362,9 +367,9 @@ struct G2Shared {
     float a[G2_S][2][A_STAGE_FLOATS];  // [stage][hi/lo] weight images (bulk copies)
     float b[G2_S][2][B_STAGE_FLOATS];  // [stage][hi/lo] activation images (written by the transform warps)
     float raw[G2_RS][TKB][TN];         // raw fp32 activation rows (bulk copies)
-    float epi[4][32 * 33];             // per epilogue warp: 32 x 32 transpose tile for channel-major stores
-    long long col_base[TN];            // output offset of every tile column (-1 = out of range)
-    long long col_bias[TN];
+    float epi[4 * G2_EPI_GROUPS][32 * 33];  // per epilogue warp: 32 x 32 transpose tile for ragged channel-major stores
+    long long col_base[G2_EPI_GROUPS][TN];  // per epilogue group: output offset of every tile column (-1 = out of range)
+    long long col_bias[G2_EPI_GROUPS][TN];
     uint64_t full_a[G2_S], full_b[G2_S], empty[G2_S], raw_full[G2_RS], raw_empty[G2_RS], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
 };
@@ -538,44 +543,50 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
         }
     } else {
         // ================================================================ epilogue: TMEM -> registers -> global
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-            const int acc = lt & 1, mt = tile % n_mt;
+        // Group eg (warps 4 eg .. 4 eg + 3) owns accumulator buffer eg: the CTA's tiles eg, eg + 2, ...  A warp reads the
+        // 32 TMEM lanes (= tile rows) of its quadrant (w & 3).
+        const int eg = w >> 2, wq = w & 3, te = t & 127;
+        long long* col_base = sh.col_base[eg];
+        long long* col_bias = sh.col_bias[eg];
+        const long long r3 = (long long)a.R * 3;
+        int use = 0;
+        for (int tile = blockIdx.x + eg * (int)gridDim.x; tile < n_tiles; tile += G2_EPI_GROUPS * (int)gridDim.x, ++use) {
+            const int mt = tile % n_mt;
             const long long c0 = (long long)(tile / n_mt) * tn;
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the previous tile's column tables are no longer read
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");  // the previous tile's column tables are no longer read
             {
-                const long long j = c0 + t;
+                const long long j = c0 + te;
                 long long base = -1, boff = 0;
-                if (t < tn && j < ncols) {
+                if (te < tn && j < ncols) {
                     const long long b = j / a.n_per_b;
                     const int n = (int)(j - b * a.n_per_b);
                     const int axis = a.npts > 0 ? n / a.npts : 0;
                     if (PM) {
                         const int pt = n - axis * a.npts;
-                        base = (b * a.npts + pt) * ((long long)a.R * 3) + (long long)axis * a.c_out;
+                        base = (b * a.npts + pt) * r3 + (long long)axis * a.c_out;
                     } else {
                         base = b * a.o_sb + n;
                         boff = b * a.bias_sb + (a.bias_axis ? axis : 0);
                     }
                 }
-                sh.col_base[t] = base;
-                sh.col_bias[t] = boff;
+                col_base[te] = base;
+                col_bias[te] = boff;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(&sh.tmem_full[acc], (lt >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
             const int r0 = mt * TM;
-            const int r = r0 + w * 32 + lane;  // TMEM lane == tile row
+            const int r = r0 + wq * 32 + lane;  // TMEM lane == tile row
             const bool row_ok = r < a.R;
             long long row_off = 0;
             if (PM) {
                 const int part = row_ok ? r / a.c_out : 0;
                 row_off = (long long)part * 3 * a.c_out + (r - part * a.c_out);
             }
+            mbar_wait(&sh.tmem_full[eg], use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int cc = 0; cc < tn; cc += 32) {
                 uint32_t v[32];
-                const uint32_t taddr = tmem + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * TN + cc);
+                const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(eg * TN + cc);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -585,76 +596,97 @@ __global__ void __launch_bounds__(G2_THREADS, 1) k_gemm_tc2(const GemmArgs a, co
                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr)
                     : "memory");
+                // the chunk's column geometry (warp uniform) and its bias are fetched while the TMEM load is in flight
+                const long long b0 = col_base[cc], b31 = col_base[cc + 31];
+                bool fast;
+                float bias0 = 0.f;
+                if (PM) {
+                    // 32 valid columns = 32 consecutive points of one (instance, axis): rows r3 floats apart
+                    fast = b0 >= 0 && b31 - b0 == 31 * r3;
+                } else {
+                    // 32 valid columns, contiguous in the output, 16-byte aligned, one bias offset for the whole chunk
+                    const long long bo0 = col_bias[cc];
+                    fast = b0 >= 0 && b31 - b0 == 31 && ((b0 | a.o_sr) & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                           (a.mask == nullptr || (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0) &&
+                           (a.bias == nullptr || bo0 == col_bias[cc + 31]);
+                    if (fast && a.bias && row_ok) bias0 = __ldg(a.bias + bo0 + (long long)r * a.bias_sr);
+                }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cc == tn - 32) {  // this thread's last read of the buffer: hand it back to the MMA warp
+                if (cc + 32 >= tn) {  // this thread's last read of the buffer: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&sh.tmem_empty[acc]);
+                    mbar_arrive(&sh.tmem_empty[eg]);
                 }
                 if (PM) {
                     if (row_ok) {
+                        if (fast) {
+                            float* o = a.out + b0 + row_off;  // lanes = consecutive channels: 128 B per warp store
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const long long base = sh.col_base[cc + j];
-                            if (base >= 0) a.out[base + row_off] = __uint_as_float(v[j]);  // lanes = consecutive channels
+                            for (int j = 0; j < 32; ++j) o[j * r3] = __uint_as_float(v[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const long long base = col_base[cc + j];
+                                if (base >= 0) a.out[base + row_off] = __uint_as_float(v[j]);
+                            }
+                        }
+                    }
+                } else if (fast) {
+                    // every thread stores its own row: 8 float4 = one full 128-byte line
+                    if (row_ok) {
+                        float4* o = reinterpret_cast<float4*>(a.out + b0 + (long long)r * a.o_sr);
+                        const bool relu = a.relu != 0;
+                        if (a.mask) {
+                            const float4* mk = reinterpret_cast<const float4*>(a.mask + b0 + (long long)r * a.o_sr);
+                            float4 m4[8];
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) m4[j4] = __ldg(mk + j4);
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                float x0 = __uint_as_float(v[4 * j4]) + bias0, x1 = __uint_as_float(v[4 * j4 + 1]) + bias0;
+                                float x2 = __uint_as_float(v[4 * j4 + 2]) + bias0, x3 = __uint_as_float(v[4 * j4 + 3]) + bias0;
+                                if (relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
+                                o[j4] = make_float4(m4[j4].x > 0.f ? x0 : 0.f, m4[j4].y > 0.f ? x1 : 0.f, m4[j4].z > 0.f ? x2 : 0.f,
+                                                    m4[j4].w > 0.f ? x3 : 0.f);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                float x0 = __uint_as_float(v[4 * j4]) + bias0, x1 = __uint_as_float(v[4 * j4 + 1]) + bias0;
+                                float x2 = __uint_as_float(v[4 * j4 + 2]) + bias0, x3 = __uint_as_float(v[4 * j4 + 3]) + bias0;
+                                if (relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
+                                o[j4] = make_float4(x0, x1, x2, x3);
+                            }
                         }
                     }
                 } else {
-                    // channel-major.  Bias + ReLU are applied while lane == row (the bias offset of a column is warp
-                    // uniform and rarely changes inside a chunk: one cached load instead of a dependent load per element).
+                    // ragged chunk (tile edge, instance boundary inside the chunk, unaligned output): bias + ReLU while
+                    // lane == row, then transpose the warp's 32 x 32 block so that lanes store consecutive columns
+                    float* tl = &sh.epi[w][0];
                     float bcache = 0.f;
                     long long last_bo = -1;
-                    float val[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        val[j] = __uint_as_float(v[j]);
+                        float x = __uint_as_float(v[j]);
                         if (a.bias) {
-                            const long long bo = sh.col_bias[cc + j];
+                            const long long bo = col_bias[cc + j];
                             if (bo != last_bo) {
                                 bcache = row_ok ? __ldg(a.bias + bo + (long long)r * a.bias_sr) : 0.f;
                                 last_bo = bo;
                             }
-                            val[j] += bcache;
+                            x += bcache;
                         }
-                        if (a.relu) val[j] = fmaxf(val[j], 0.f);
+                        if (a.relu) x = fmaxf(x, 0.f);
+                        tl[lane * 33 + j] = x;
                     }
-                    const long long b0 = sh.col_base[cc], b31 = sh.col_base[cc + 31];
-                    // fast path (warp uniform): the chunk's 32 columns are valid, contiguous in the output and 16-byte
-                    // aligned -> every thread stores its own row as 8 float4 (no transpose through shared memory)
-                    const bool vec = b0 >= 0 && b31 - b0 == 31 && ((b0 | a.o_sr) & 3) == 0 &&
-                                     (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
-                                     (a.mask == nullptr || (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0);
-                    if (vec) {
-                        if (row_ok) {
-                            float4* o = reinterpret_cast<float4*>(a.out + b0 + (long long)r * a.o_sr);
-                            if (a.mask) {
-                                const float4* mk = reinterpret_cast<const float4*>(a.mask + b0 + (long long)r * a.o_sr);
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; ++j4) {
-                                    const float4 m4 = __ldg(mk + j4);
-                                    o[j4] = make_float4(m4.x > 0.f ? val[4 * j4] : 0.f, m4.y > 0.f ? val[4 * j4 + 1] : 0.f,
-                                                        m4.z > 0.f ? val[4 * j4 + 2] : 0.f, m4.w > 0.f ? val[4 * j4 + 3] : 0.f);
-                                }
-                            } else {
-#pragma unroll
-                                for (int j4 = 0; j4 < 8; ++j4)
-                                    o[j4] = make_float4(val[4 * j4], val[4 * j4 + 1], val[4 * j4 + 2], val[4 * j4 + 3]);
-                            }
-                        }
-                    } else {
-                        // general path: transpose the warp's 32 x 32 block so that lanes store consecutive columns
-                        float* tl = &sh.epi[w][0];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) tl[lane * 33 + j] = val[j];
-                        __syncwarp();
-                        const long long base = sh.col_base[cc + lane];
-                        if (base >= 0) {
-                            const int nrow = min(32, a.R - (r0 + w * 32));
-                            for (int rr = 0; rr < nrow; ++rr) {
-                                const long long oo = base + (long long)(r0 + w * 32 + rr) * a.o_sr;
-                                float x = tl[rr * 33 + lane];
-                                if (a.mask && !(__ldg(a.mask + oo) > 0.f)) x = 0.f;
-                                a.out[oo] = x;
-                            }
+                    __syncwarp();
+                    const long long base = col_base[cc + lane];
+                    if (base >= 0) {
+                        const int nrow = min(32, a.R - (r0 + wq * 32));
+                        for (int rr = 0; rr < nrow; ++rr) {
+                            const long long oo = base + (long long)(r0 + wq * 32 + rr) * a.o_sr;
+                            float x = tl[rr * 33 + lane];
+                            if (a.mask && !(__ldg(a.mask + oo) > 0.f)) x = 0.f;
+                            a.out[oo] = x;
                         }
                     }
                     __syncwarp();
