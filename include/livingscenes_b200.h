@@ -158,8 +158,10 @@ LS_API int ls_set_knn_tensor_cores(int32_t on, float kappa_scale);
  * side stream next to the kNN chain (fork/join with events; capturable).  0: everything on the caller's stream. */
 LS_API int ls_set_overlap(int32_t on);
 LS_API int ls_set_tensor_cores(int32_t on);   /* 1 (default): use the tcgen05 path where packed weights exist */
-/* 2 (default): persistent warp-specialised tcgen05 GEMM (bulk-TMA fed, double-buffered TMEM); 1: the round-1
- * one-CTA-per-tile kernel (kept for A/B measurements).  Process-global, like the other ls_set_* switches. */
+/* 3 (default): tcgen05 GEMM with the activations in tensor memory (TS-form MMAs, 256-row weight tiles for K >= 128);
+ * 2: persistent warp-specialised kernel with both operands in shared memory (bulk-TMA fed, double-buffered TMEM);
+ * 1: the round-1 one-CTA-per-tile kernel (2 and 1 kept for A/B measurements).  Process-global, like the other
+ * ls_set_* switches. */
 LS_API int ls_set_gemm_variant(int32_t variant);
 /* FPS squared distance: 0 (default) dx*dx + dy*dy + dz*dz with every product and sum rounded to fp32 (pytorch3d's
  * CPU path, the oracle and the committed fixtures); 1: fma(dz,dz,fma(dy,dy,dx*dx)), what nvcc's default contraction

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "_ls_b200.so")
-SOURCES = ["ls_encoder.cu", "ls_gemm.cu", "ls_gemm_tc.cu", "ls_knn_tc.cu", "ls_solvers.cu", "ls_sdf.cu", "ls_sdf_bwd.cu", "ls_mesh.cu"]
+SOURCES = ["ls_encoder.cu", "ls_gemm.cu", "ls_gemm_tc.cu", "ls_gemm_tc3.cu", "ls_knn_tc.cu", "ls_solvers.cu", "ls_sdf.cu", "ls_sdf_bwd.cu", "ls_mesh.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 NVCC_FLAGS += os.environ.get("LS_NVCC_EXTRA", "").split()  # experiment knobs (-D...), part of the object digest

@@ -201,7 +201,8 @@ def set_tensor_cores(on: bool) -> None:
 
 
 def set_gemm_variant(variant: int) -> None:
-    """2 (default): persistent warp-specialised tcgen05 GEMM; 1: the round-1 one-CTA-per-tile kernel."""
+    """3 (default): activations in tensor memory (TS-form MMAs, 256-row weight tiles for K >= 128); 2: persistent
+    warp-specialised kernel with both operands in shared memory; 1: the round-1 one-CTA-per-tile kernel."""
     check(lib().ls_set_gemm_variant(int(variant)), "ls_set_gemm_variant")
 
 

@@ -133,7 +133,11 @@ size_t tc_packed_floats(int R, int K);
 int tc_pack_weights(const float* W, int R, int K, int ldw, float* packed, cudaStream_t st);
 bool gemm_tc_supported(const GemmArgs& a);
 int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st);
+// TS-form variant (ls_gemm_tc3.cu): activations in tensor memory, 128- or 256-row weight tiles
+size_t tc3_packed_floats(int R, int K);
+int tc3_pack_weights(const float* W, int R, int K, int ldw, float* packed256, cudaStream_t st);
+int launch_gemm_tc3(const GemmArgs& a, const float* packed128, const float* packed256, cudaStream_t st);
 extern bool g_use_tensor_cores;
-extern int g_gemm_variant;  // 2 = persistent warp-specialised k_gemm_tc2 (default), 1 = round-1 k_gemm_tc
+extern int g_gemm_variant;  // 3 = k_gemm_tc3 (TS form, default), 2 = persistent SS-form k_gemm_tc2, 1 = round-1 k_gemm_tc
 
 }  // namespace ls

@@ -780,7 +780,8 @@ int ls_set_wave_bytes(int64_t bytes) {
     return LS_OK;
 }
 int ls_set_gemm_variant(int32_t variant) {
-    LS_REQUIRE(variant == 1 || variant == 2, "gemm variant must be 1 (per-tile CTAs) or 2 (persistent, warp-specialised)");
+    LS_REQUIRE(variant >= 1 && variant <= 3,
+               "gemm variant must be 1 (per-tile CTAs), 2 (persistent, operands in shared memory) or 3 (activations in tensor memory)");
     ls::g_gemm_variant = variant;
     return LS_OK;
 }

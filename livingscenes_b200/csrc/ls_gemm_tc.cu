@@ -721,10 +721,13 @@ __global__ void k_tc_pack_weights(const float* __restrict__ W, int R, int K, int
 
 }  // namespace
 
-size_t tc_packed_floats(int R, int K) {
+// 128-row-tile images (k_gemm_tc, k_gemm_tc2, k_gemm_tc3 with NT = 128), followed by the 256-row-tile images of
+// k_gemm_tc3 (ls_gemm_tc3.cu) when R > 128
+static size_t tc128_floats(int R, int K) {
     const size_t mt = (R + TM - 1) / TM, kb = (K + TKB - 1) / TKB;
     return mt * kb * 2 * A_STAGE_FLOATS;
 }
+size_t tc_packed_floats(int R, int K) { return tc128_floats(R, K) + tc3_packed_floats(R, K); }
 
 int tc_pack_weights(const float* W, int R, int K, int ldw, float* packed, cudaStream_t st) {
     LS_REQUIRE(W && packed && R > 0 && K > 0 && ldw >= K, "tc_pack_weights: bad arguments");
@@ -732,7 +735,7 @@ int tc_pack_weights(const float* W, int R, int K, int ldw, float* packed, cudaSt
     dim3 grid(n_kb, (R + TM - 1) / TM);
     k_tc_pack_weights<<<grid, 256, 0, st>>>(W, R, K, ldw, packed, n_kb);
     LS_CHECK_LAUNCH("k_tc_pack_weights");
-    return LS_OK;
+    return tc3_pack_weights(W, R, K, ldw, packed + tc128_floats(R, K), st);
 }
 
 bool gemm_tc_supported(const GemmArgs& a) {
@@ -742,10 +745,12 @@ bool gemm_tc_supported(const GemmArgs& a) {
     return true;
 }
 
-// 2: persistent warp-specialised k_gemm_tc2; 1: round-1 k_gemm_tc (env LS_GEMM_VARIANT for A/B runs)
+// 3: k_gemm_tc3 (activations in tensor memory, TS-form MMAs; default); 2: persistent warp-specialised k_gemm_tc2 (both
+// operands in shared memory); 1: round-1 k_gemm_tc (env LS_GEMM_VARIANT for A/B runs)
 int g_gemm_variant = [] {
     const char* e = getenv("LS_GEMM_VARIANT");
-    return (e && atoi(e) == 1) ? 1 : 2;
+    const int v = e ? atoi(e) : 3;
+    return (v >= 1 && v <= 3) ? v : 3;
 }();
 
 static int sm_count() {
@@ -817,13 +822,22 @@ int launch_gemm_tc(const GemmArgs& a, const float* packed, cudaStream_t st) {
     if (a.point_major)
         LS_REQUIRE(a.c_out % 32 == 0 && a.R % a.c_out == 0 && a.npts > 0 && a.n_per_b == 3 * a.npts,
                    "gemm_tc: bad point-major geometry");
+    // Dispatch by geometry: short contractions (K < 128: the table GEMMs of layers 1-4, the global conv of layers 2-3)
+    // are epilogue / store bound and measured 10-30 % faster on k_gemm_tc2; K >= 128 (SDF decoder, deep encoder layers,
+    // head) is MMA bound and runs 1.2-1.7x faster with the TS form (profiles/r02/experiments.md).  LS_GEMM_V3_MIN_K: A/B.
+    static const int v3_min_k = [] {
+        const char* e = getenv("LS_GEMM_V3_MIN_K");
+        return e ? atoi(e) : 128;
+    }();
+    if (g_gemm_variant == 3 && a.K >= v3_min_k)
+        return launch_gemm_tc3(a, packed, a.R > 128 ? packed + tc128_floats(a.R, a.K) : nullptr, st);
     const long long ncols = (long long)a.B * a.n_per_b;
     const int n_kb = (a.K + TKB - 1) / TKB;
     // the dynamic shared-memory opt-in is per device: set it on every launch (cheap, legal under stream capture)
     // instead of caching a process-wide flag that a second device in the same process would never see
     const int tn = gemm_v2_tile_cols(a);
     const long long tiles_all = tn ? ((ncols + tn - 1) / tn) * ((a.R + TM - 1) / TM) : 0;
-    if (g_gemm_variant == 1 || tn == 0 || tiles_all < 2LL * sm_count()) {
+    if (g_gemm_variant == 1 || tn == 0 || tiles_all < 2LL * sm_count()) {  // (variant 3 below its K threshold runs as variant 2)
         dim3 grid((unsigned)((ncols + TN - 1) / TN), (unsigned)((a.R + TM - 1) / TM));
         const size_t smem = sizeof(TcShared) + 128;
         if (a.point_major) {

@@ -64,10 +64,10 @@ q = ((torch.rand(64, M, 3, generator=torch.Generator().manual_seed(5)) - 0.5) * 
 ms = timed(lambda: model.decoder(q, None, codes, return_sdf=True), n=5, warm=2)
 flops = 64 * M * 2 * (257 * 768 + 2 * 768 * 768 + 768 * 255 + 512 * 768 + 3 * 768 * 768 + 768)
 out["config5_sdf_64x100k"] = {"ms": ms, "points_per_s": 64 * M / ms * 1e3, "TFLOPs_fp32_equiv": flops / ms * 1e-9,
-                              "tensor_TFLOPs_tf32_issued": 3 * flops / ms * 1e-9, "gemm": "persistent tcgen05 (variant 2)"}
+                              "tensor_TFLOPs_tf32_issued": 3 * flops / ms * 1e-9, "gemm": "tcgen05 TS form (variant 3)"}
 _lib.set_gemm_variant(1)
 ms1 = timed(lambda: model.decoder(q, None, codes, return_sdf=True), n=5, warm=2)
-_lib.set_gemm_variant(2)
+_lib.set_gemm_variant(3)
 out["config5_sdf_64x100k_gemm_variant1"] = {"ms": ms1, "points_per_s": 64 * M / ms1 * 1e3, "tensor_TFLOPs_tf32_issued": 3 * flops / ms1 * 1e-9}
 _lib.set_tensor_cores(False)
 ms2 = timed(lambda: model.decoder(q[:8], None, {k: v[:8] for k, v in codes.items()}, return_sdf=True), n=3, warm=1)

@@ -418,12 +418,19 @@ def test_gemm_persistent_equals_per_tile_kernel(B, Ci, Co, N, dev):
         a = ls.vn_linear(W, v, tensor_cores=True)
         _lib.set_gemm_variant(2)
         b = ls.vn_linear(W, v, tensor_cores=True)
+        _lib.set_gemm_variant(3)
+        c = ls.vn_linear(W, v, tensor_cores=True)
         torch.cuda.synchronize()
     finally:
-        _lib.set_gemm_variant(2)
+        _lib.set_gemm_variant(3)
     assert torch.equal(a, b)
     ref = torch.einsum("oc,bcan->boan", W.double().cpu(), v.double().cpu())
     assert float((b.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    # variant 3 (activations in tensor memory, operand roles swapped, 256-row weight tiles for K >= 128): the same three
+    # TF32 products per k-step, fp32-accurate like the others
+    assert c.shape == b.shape
+    assert float((c.cpu().double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((c - b).abs().max() / b.abs().max()) < 4e-6
 
 
 def test_encoder_wave_schedule_invariance(dev, oracle_R):
@@ -434,26 +441,32 @@ def test_encoder_wave_schedule_invariance(dev, oracle_R):
     enc = _model("random", dev).encoder
     x = oracle_R.synth_instances(23, 1024, 777).to(dev)
     try:
-        _lib.set_wave_bytes(0)
-        ref = enc.run(x, normalize=True, taps=True)
-        torch.cuda.synchronize()
-        for wave_mb, overlap, variant in ((28, True, 2), (6, True, 2), (6, False, 2), (12, True, 1), (1, True, 2)):
-            _lib.set_wave_bytes(wave_mb << 20)
-            _lib.set_overlap(overlap)
-            _lib.set_gemm_variant(variant)
-            for _ in range(2):
-                r = enc.run(x, normalize=True, taps=True)
+        # variants 1 and 2 issue identical MMAs (bit-identical to each other); variant 3 swaps the operand roles and is
+        # compared with itself
+        for ref_variant, cases in ((2, ((28, True, 2), (6, True, 2), (6, False, 2), (12, True, 1), (1, True, 2))),
+                                   (3, ((28, True, 3), (6, False, 3), (1, True, 3)))):
+            _lib.set_wave_bytes(0)
+            _lib.set_overlap(True)
+            _lib.set_gemm_variant(ref_variant)
+            ref = enc.run(x, normalize=True, taps=True)
             torch.cuda.synchronize()
-            for i, (ia, ib) in enumerate(zip(ref["knn_idx"], r["knn_idx"])):
-                assert torch.equal(ia, ib), f"layer {i} wave_mb={wave_mb}"
-            for i, (fa, fb) in enumerate(zip(ref["feat"], r["feat"])):
-                assert torch.equal(fa, fb), f"features of layer {i} wave_mb={wave_mb} overlap={overlap} variant={variant}"
-            for k in ("z_so3", "z_inv", "scale", "center"):
-                assert torch.equal(ref[k], r[k]), k
+            for wave_mb, overlap, variant in cases:
+                _lib.set_wave_bytes(wave_mb << 20)
+                _lib.set_overlap(overlap)
+                _lib.set_gemm_variant(variant)
+                for _ in range(2):
+                    r = enc.run(x, normalize=True, taps=True)
+                torch.cuda.synchronize()
+                for i, (ia, ib) in enumerate(zip(ref["knn_idx"], r["knn_idx"])):
+                    assert torch.equal(ia, ib), f"layer {i} wave_mb={wave_mb}"
+                for i, (fa, fb) in enumerate(zip(ref["feat"], r["feat"])):
+                    assert torch.equal(fa, fb), f"features of layer {i} wave_mb={wave_mb} overlap={overlap} variant={variant}"
+                for k in ("z_so3", "z_inv", "scale", "center"):
+                    assert torch.equal(ref[k], r[k]), k
     finally:
         _lib.set_wave_bytes(0)
         _lib.set_overlap(True)
-        _lib.set_gemm_variant(2)
+        _lib.set_gemm_variant(3)
 
 
 # ------------------------------------------------------------------------------------------ encoder
