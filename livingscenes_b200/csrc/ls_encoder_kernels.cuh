@@ -1306,8 +1306,11 @@ __device__ __forceinline__ unsigned ord_f32(float f) {  // order-preserving map 
 }
 // DP > 0: the padded feature dimension is a compile-time constant (8 / 96 / 192 on the shipped model): the row
 // loops unroll and the row addresses become constant strides; DP == 0 reads it from the arguments.
+#ifndef LS_RR_CTAS
+#define LS_RR_CTAS 2  // 3 / 4 CTAs per SM measured slower (80 / 64 registers spill: profiles/r02/experiments.md)
+#endif
 template <int DP>
-__global__ void __launch_bounds__(RR_WARPS * 32, 2) k_knn_rerank(const RerankArgs a) {
+__global__ void __launch_bounds__(RR_WARPS * 32, LS_RR_CTAS) k_knn_rerank(const RerankArgs a) {
     const int Dp = DP > 0 ? DP : a.Dp;
     __shared__ __align__(16) float sq_all[RR_WARPS][4 * RR_F4];
     __shared__ u64 ssort[RR_WARPS][64];

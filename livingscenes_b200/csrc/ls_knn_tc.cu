@@ -51,7 +51,10 @@ constexpr int KT_STAGES = KT_STAGES_N;
 constexpr int KT_STASH = KT_STASH_N;    // shared-memory stash slots per query
 constexpr int KT_THREADS = 160;
 constexpr int KT_TMEM_COLS = KT_GT * KT_PTS;  // 256 columns: two CTAs share an SM's tensor memory
-constexpr int KT_MIN_CTAS = KT_GT <= 2 ? 2 : 1;
+#ifndef KT_MIN_CTAS_N
+#define KT_MIN_CTAS_N (KT_GT_N <= 2 ? 2 : 1)
+#endif
+constexpr int KT_MIN_CTAS = KT_MIN_CTAS_N;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
