@@ -644,24 +644,11 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             k_row_mean<<<dim3((Co * 3 + 7) / 8, B), 256, 0, st>>>(p.pooled, Co * 3, Nd, p.gmean);
             LS_CHECK_LAUNCH("k_row_mean");
             if (Co >= 128) {
-                // bias[b][r][a] = sum_c Wg2[r][c] g[b][c][a] as ONE batched FP32 GEMM over all instances (R = 2 Co rows,
-                // 3 B columns): the per-(instance, 8 rows) gemv CTAs re-read the 2 MB weight matrix 256 times (0.12 ms at
-                // layer 6 for 0.8 GFLOP)
-                GemmArgs gb{};
-                gb.W = L.w_g2;
-                gb.R = 2 * Co;
-                gb.K = Co;
-                gb.ldw = Co;
-                gb.B = B;
-                gb.X = p.gmean;
-                gb.n_per_b = 3;
-                gb.x_sb = (long long)Co * 3;
-                gb.x_sk = 3;
-                gb.out = p.bias;
-                gb.o_sb = 2LL * Co * 3;
-                gb.o_sr = 3;
-                rc = launch_gemm_simt(gb, st);
-                if (rc != LS_OK) return rc;
+                // bias[b][r][a] = sum_c Wg2[r][c] g[b][c][a]: a warp per weight row, 8 instances per CTA
+                const size_t smem = (size_t)BIAS_BG * Co * 3 * sizeof(float);
+                LS_CHECK_CUDA(cudaFuncSetAttribute(k_bias_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_bias_rows<<<dim3((2 * Co + 8 * BIAS_RPW - 1) / (8 * BIAS_RPW), (B + BIAS_BG - 1) / BIAS_BG), 256, smem, st>>>(p.gmean, Co, B, L.w_g2, p.bias);
+                LS_CHECK_LAUNCH("k_bias_rows");
             } else {
                 k_bias_gemv<<<dim3((2 * Co + 7) / 8, B), 256, (size_t)Co * 3 * sizeof(float), st>>>(p.gmean, Co, L.w_g2, p.bias);
                 LS_CHECK_LAUNCH("k_bias_gemv");
@@ -687,8 +674,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             g.bias_axis = 1;
             rc = launch_gemm(g, st);
             if (rc != LS_OK) return rc;
-            dim3 gv((Nd + 127) / 128, Co, B);
-            k_vnact<<<gv, 128, 0, st>>>(p.raw, Co, Nd, oms, layer_out);
+            k_vnact<<<dim3((Co * Nd + 255) / 256, B), 256, 0, st>>>(p.raw, Co, Nd, oms, layer_out);
             LS_CHECK_LAUNCH("k_vnact");
         }
         if (io->feat[i])

@@ -1439,11 +1439,56 @@ __global__ void __launch_bounds__(256) k_bias_gemv(const float* __restrict__ g, 
     }
 }
 
-// raw [B][2Co][3][N] (q rows, then direction rows) -> VN leaky-ReLU -> out [B][Co][3][N]
-__global__ void k_vnact(const float* __restrict__ raw, int Co, int N, float oms, float* __restrict__ out) {
-    const int b = blockIdx.z, c = blockIdx.y;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// The same bias for BG instances per CTA: a warp owns one weight row and reads it ONCE for the BG instances whose
+// pooled means sit in shared memory (the per-instance gemv re-read the 2 MB matrix of layer 6 for each of the 256
+// instances; the 48-CTA SIMT GEMM that replaced it in round 2 ran 0.11 ms for 0.8 GFLOP).  Accumulation order per
+// (instance, row): lanes stride the channels, then a shuffle tree -- independent of the batch composition.
+constexpr int BIAS_BG = 8, BIAS_RPW = 8;
+__global__ void __launch_bounds__(256) k_bias_rows(const float* __restrict__ g, int Co, int B, const float* __restrict__ wg2,
+                                                   float* __restrict__ bias) {
+    extern __shared__ float sg[];  // [BIAS_BG][Co*3]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b0 = blockIdx.y * BIAS_BG, nb = min(BIAS_BG, B - b0);
+    for (int i = threadIdx.x; i < BIAS_BG * Co * 3; i += blockDim.x)
+        sg[i] = (i / (Co * 3) < nb) ? g[(size_t)b0 * Co * 3 + i] : 0.f;
+    __syncthreads();
+#pragma unroll 1
+    for (int rr = 0; rr < BIAS_RPW; ++rr) {  // the staged means are reused for BIAS_RPW rows per warp
+        const int r = (blockIdx.x * 8 + w) * BIAS_RPW + rr;
+        if (r >= 2 * Co) return;
+        float acc[BIAS_BG][3];
+#pragma unroll
+        for (int bi = 0; bi < BIAS_BG; ++bi) acc[bi][0] = acc[bi][1] = acc[bi][2] = 0.f;
+        for (int c = lane; c < Co; c += 32) {
+            const float wv = __ldg(wg2 + (size_t)r * Co + c);
+#pragma unroll
+            for (int bi = 0; bi < BIAS_BG; ++bi) {
+                const float* gp = sg + bi * Co * 3 + c * 3;
+                acc[bi][0] = fmaf(wv, gp[0], acc[bi][0]);
+                acc[bi][1] = fmaf(wv, gp[1], acc[bi][1]);
+                acc[bi][2] = fmaf(wv, gp[2], acc[bi][2]);
+            }
+        }
+#pragma unroll
+        for (int bi = 0; bi < BIAS_BG; ++bi) {
+            const float s0 = warp_sum(acc[bi][0]), s1 = warp_sum(acc[bi][1]), s2 = warp_sum(acc[bi][2]);
+            if (lane == 0 && bi < nb) {
+                float* o = bias + ((size_t)(b0 + bi) * 2 * Co + r) * 3;
+                o[0] = s0;
+                o[1] = s1;
+                o[2] = s2;
+            }
+        }
+    }
+}
+
+// raw [B][2Co][3][N] (q rows, then direction rows) -> VN leaky-ReLU -> out [B][Co][3][N]; thread = (channel, point)
+// flattened, so that the deep layers (N = 32) still run full warps
+__global__ void __launch_bounds__(256) k_vnact(const float* __restrict__ raw, int Co, int N, float oms, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Co * N) return;
+    const int c = e / N, n = e - c * N;
     const float* q = raw + ((size_t)b * 2 * Co + c) * 3 * N + n;
     const float* k = raw + ((size_t)b * 2 * Co + Co + c) * 3 * N + n;
     float o0, o1, o2;

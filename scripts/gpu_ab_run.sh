@@ -1,1 +1,1 @@
-bash scripts/gpu_ab_variants.sh base rr3 rr4 kt1
+bash scripts/gpu_ab_variants.sh s3 g1s4
