@@ -293,16 +293,25 @@ int pick_qpc(int B, int Nd, bool phase2_only, int Co = 0, size_t table_bytes = 0
     return qpc;
 }
 
-int launch_rerank(const RerankArgs& ra, int B, cudaStream_t st) {
-    const dim3 grid((ra.Nd + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B);
+template <bool FB>
+int launch_rerank_one(const RerankArgs& ra, dim3 grid, cudaStream_t st) {
     switch (ra.Dp) {
-        case 8: k_knn_rerank<8><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
-        case 96: k_knn_rerank<96><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
-        case 192: k_knn_rerank<192><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
-        default: k_knn_rerank<0><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        case 8: k_knn_rerank<8, FB><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        case 96: k_knn_rerank<96, FB><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        case 192: k_knn_rerank<192, FB><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
+        default: k_knn_rerank<0, FB><<<grid, RR_WARPS * 32, 0, st>>>(ra); break;
     }
     LS_CHECK_LAUNCH("k_knn_rerank");
     return LS_OK;
+}
+// two launches: the common path at 3 CTAs per SM, then the rare heavy paths (CTAs without a flagged query exit at once)
+int launch_rerank(const RerankArgs& ra, int B, cudaStream_t st) {
+    const dim3 grid((ra.Nd + RR_WARPS * RR_QPW - 1) / (RR_WARPS * RR_QPW), B);
+    if (!ra.all_exact) {
+        const int rc = launch_rerank_one<false>(ra, grid, st);
+        if (rc != LS_OK) return rc;
+    }
+    return launch_rerank_one<true>(ra, grid, st);
 }
 
 int launch_edge(int mode, const EdgeArgs& a, cudaStream_t st) {

@@ -1306,19 +1306,33 @@ __device__ __forceinline__ unsigned ord_f32(float f) {  // order-preserving map 
 }
 // DP > 0: the padded feature dimension is a compile-time constant (8 / 96 / 192 on the shipped model): the row
 // loops unroll and the row addresses become constant strides; DP == 0 reads it from the arguments.
+// FB = false: the common path (0 <= count <= 32, no distances wanted) ONLY; FB = true: the rare heavy paths only (overflowed
+// lists -> exact brute force, lists longer than 32 or all_exact -> exact distance for every candidate).  One kernel with
+// all three paths needs 128 registers (16 warps per SM) for a latency-bound warp-per-query loop; the common path alone
+// needs 64-80 and runs at 4 CTAs per SM (measured: re-rank 1.07 ms -> 0.94 at 3 CTAs -> 0.90 at 4).  The FB launch exits per
+// CTA when none of its 32 queries is flagged.
 #ifndef LS_RR_CTAS
-#define LS_RR_CTAS 2  // 3 / 4 CTAs per SM measured slower (80 / 64 registers spill: profiles/r02/experiments.md)
+#define LS_RR_CTAS 4
 #endif
-template <int DP>
-__global__ void __launch_bounds__(RR_WARPS * 32, LS_RR_CTAS) k_knn_rerank(const RerankArgs a) {
+template <int DP, bool FB>
+__global__ void __launch_bounds__(RR_WARPS * 32, FB ? 2 : LS_RR_CTAS) k_knn_rerank(const RerankArgs a) {
     const int Dp = DP > 0 ? DP : a.Dp;
     __shared__ __align__(16) float sq_all[RR_WARPS][4 * RR_F4];
     __shared__ u64 ssort[RR_WARPS][64];
     __shared__ __align__(16) float scoop[RR_WARPS][(1 + RR_NR) * RR_ROW];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.y, qbase = (blockIdx.x * RR_WARPS + w) * RR_QPW;
-    if (qbase >= a.Nd) return;
     const int n_pt_q = (a.Nd + KT_PTS - 1) / KT_PTS;
+    if (FB && !a.all_exact) {  // CTA-level early exit: is any of this CTA's RR_WARPS * RR_QPW queries flagged?
+        const int q = blockIdx.x * RR_WARPS * RR_QPW + (int)threadIdx.x;
+        int flagged = 0;
+        if (threadIdx.x < RR_WARPS * RR_QPW && q < a.Nd) {
+            const int c = __ldg(a.cand_cnt + ((size_t)b * n_pt_q + q / KT_PTS) * KT_PTS + q % KT_PTS);
+            flagged = c < 0 || c > 32;
+        }
+        if (!__syncthreads_or(flagged)) return;
+    }
+    if (qbase >= a.Nd) return;
     const float* pms = a.pm_s + (size_t)b * a.Ns * Dp;
     float* sq = sq_all[w];
     // software pipeline over the warp's queries: the next query's list is in flight while this one is processed
@@ -1344,16 +1358,21 @@ __global__ void __launch_bounds__(RR_WARPS * 32, LS_RR_CTAS) k_knn_rerank(const 
         const float* qrow = a.pm_q + ((size_t)b * a.Nd + q) * Dp;
         int s_out;
         float d_out = 0.f;
-        if (c_j < 0) {
+        const bool heavy = c_j < 0 || c_j > 32 || a.all_exact;
+        if (heavy != FB) continue;  // the other launch's query
+        if (!FB) {
+            // (common path below)
+        } else if (c_j < 0) {
             const u64 lk = knn_bruteforce_pm(qrow, sq, pms, a.Ns, Dp);
             s_out = key_idx(lk) & 0x7fffffff;
             d_out = key_dist(lk);
-        } else if (c_j > 32 || a.all_exact) {
+        } else {
             const int qt = q / KT_PTS;
             const u64 lk = knn_rerank(qrow, sq, pms, a.cand + ((size_t)b * n_pt_q + qt) * KT_CAP * KT_PTS + q % KT_PTS, c_j, Dp);
             s_out = key_idx(lk) & 0x7fffffff;
             d_out = key_dist(lk);
-        } else {
+        }
+        if (!FB) {
             const int cnt = c_j;
             u64 key = lane < cnt ? (((u64)ord_f32(cd_j) << 32) | (unsigned)ci_j) : KEY_MAX;
             key = warp_rank_sort(key, cnt, ssort[w]);

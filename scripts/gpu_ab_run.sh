@@ -1,1 +1,1 @@
-bash scripts/gpu_ab_variants.sh s3 g1s4
+bash scripts/gpu_ab_variants.sh rr3 rr4
