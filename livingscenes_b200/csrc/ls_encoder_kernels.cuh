@@ -57,35 +57,65 @@ __global__ void __launch_bounds__(NORM_THREADS) k_normalize(const float* __restr
     }
     __syncthreads();
 
-    // per-thread top-5 of squared distances over the rows i = t, t+T, ...
-    float top[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
-    for (int i = t; i < N; i += NORM_THREADS) {
-        const float xi = sx[i], yi = sx[N + i], zi = sx[2 * N + i];
-        for (int j = 0; j < N; ++j) {
-            float dx = xi - sx[j], dy = yi - sx[N + j], dz = zi - sx[2 * N + j];
-            float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            if (d2 > top[4]) {
-                top[4] = d2;
-#pragma unroll
-                for (int k = 4; k > 0; --k) {
-                    if (top[k] > top[k - 1]) {
-                        float tmp = top[k];
-                        top[k] = top[k - 1];
-                        top[k - 1] = tmp;
-                    }
-                }
+    // The reference takes the top-5 of the flattened SYMMETRIC matrix: every unordered pair appears twice with the same
+    // bits (d(i,j) and d(j,i) differ by exact negations only), so the top-5 is (p1, p1, p2, p2, p3) for the three largest
+    // unordered-pair values p1 >= p2 >= p3 (ties included).  Each thread therefore visits the pairs j > i of rows i and
+    // N-1-i (N-1 pairs per row pair: balanced), four j per 16-byte shared-memory load, and keeps a top-3.
+    float top[3] = {-1.f, -1.f, -1.f};
+    auto push = [&](float d2) {
+        if (d2 > top[2]) {
+            top[2] = d2;
+            if (top[2] > top[1]) {
+                const float tmp = top[2];
+                top[2] = top[1];
+                top[1] = tmp;
+            }
+            if (top[1] > top[0]) {
+                const float tmp = top[1];
+                top[1] = top[0];
+                top[0] = tmp;
             }
         }
+    };
+    auto row = [&](int i) {
+        const float xi = sx[i], yi = sx[N + i], zi = sx[2 * N + i];
+        auto one = [&](int j) {
+            const float dx = xi - sx[j], dy = yi - sx[N + j], dz = zi - sx[2 * N + j];
+            push(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        };
+        int j = i + 1;
+        if ((N & 3) == 0) {
+            for (; j < N && (j & 3) != 0; ++j) one(j);
+            for (; j + 3 < N; j += 4) {
+                const float4 xj = *reinterpret_cast<const float4*>(sx + j);
+                const float4 yj = *reinterpret_cast<const float4*>(sx + N + j);
+                const float4 zj = *reinterpret_cast<const float4*>(sx + 2 * N + j);
+                float dx = xi - xj.x, dy = yi - yj.x, dz = zi - zj.x;
+                push(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                dx = xi - xj.y, dy = yi - yj.y, dz = zi - zj.y;
+                push(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                dx = xi - xj.z, dy = yi - yj.z, dz = zi - zj.z;
+                push(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+                dx = xi - xj.w, dy = yi - yj.w, dz = zi - zj.w;
+                push(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+            }
+        }
+        for (; j < N; ++j) one(j);
+    };
+    for (int i = t; 2 * i < N; i += NORM_THREADS) {
+        row(i);
+        if (N - 1 - i != i) row(N - 1 - i);
     }
-    // merge: 5 rounds of block-wide max with removal
+    // merge: 3 rounds of block-wide max with removal
     __shared__ float s_best[NORM_THREADS / 32];
     __shared__ int s_who[NORM_THREADS / 32];
+    __shared__ float s_top3[3];
     __shared__ float s_sel[5];
     int p = 0;
-    for (int r = 0; r < 5; ++r) {
+    for (int r = 0; r < 3; ++r) {
         float cand = -1.f;
 #pragma unroll
-        for (int k = 0; k < 5; ++k)
+        for (int k = 0; k < 3; ++k)
             if (k == p) cand = top[k];
         float v = cand;
         int who = t;
@@ -112,9 +142,15 @@ __global__ void __launch_bounds__(NORM_THREADS) k_normalize(const float* __restr
             }
         }
         if (t == bw) ++p;
-        if (t == 0) s_sel[r] = bv;
+        if (t == 0) s_top3[r] = bv;
         __syncthreads();
     }
+    if (t == 0) {  // the flattened matrix holds every pair twice (a cloud of < 3 pairs pads with the diagonal's zeros)
+        s_sel[0] = s_sel[1] = s_top3[0];
+        s_sel[2] = s_sel[3] = s_top3[1];
+        s_sel[4] = s_top3[2];
+    }
+    __syncthreads();
     float s0 = 0.f;
 #pragma unroll
     for (int r = 0; r < 5; ++r) s0 += sqrtf(fmaxf(s_sel[r], 0.f));
