@@ -478,8 +478,8 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
                 fps_pending = false;
             }
             ProfScope ps(2, i, st);
-            dim3 g((Nd + 127) / 128, Ci * 3, B);
-            k_gather_points<<<g, 128, 0, st>>>(src_f, p.sel[i], Ci * 3, Ns, Nd, p.dstf);
+            dim3 g((Ci * 3 * Nd + 255) / 256, B);
+            k_gather_points<<<g, 256, 0, st>>>(src_f, p.sel[i], Ci * 3, Ns, Nd, p.dstf);
             LS_CHECK_LAUNCH("k_gather_points");
             dst_f = p.dstf;
         }
@@ -650,7 +650,7 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
         }
         if (L.global_conv) {
             ProfScope ps(5, i, st);
-            k_row_mean<<<dim3((Co * 3 + 7) / 8, B), 256, 0, st>>>(p.pooled, Co * 3, Nd, p.gmean);
+            k_row_mean<<<dim3(Nd == 32 ? (Co * 3 + 63) / 64 : (Co * 3 + 7) / 8, B), 256, 0, st>>>(p.pooled, Co * 3, Nd, p.gmean);
             LS_CHECK_LAUNCH("k_row_mean");
             if (Co >= 128) {
                 // bias[b][r][a] = sum_c Wg2[r][c] g[b][c][a]: a warp per weight row, 8 instances per CTA

@@ -433,13 +433,15 @@ __global__ void __launch_bounds__(1024) k_fps_masked(const float* __restrict__ x
 }
 
 // dst_f[b][r][j] = src_f[b][r][sel[b][j]]   (vec_dgcnn_atten.py:173; r runs over C*3 rows)
-__global__ void k_gather_points(const float* __restrict__ in, const int* __restrict__ sel, int rows,
-                                int n_in, int n_out, float* __restrict__ out) {
-    const int b = blockIdx.z, r = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_out) return;
-    int s = sel[(size_t)b * n_out + j];
-    out[((size_t)b * rows + r) * n_out + j] = in[((size_t)b * rows + r) * n_in + s];
+// thread = (row, selected point) flattened per instance, so that small n_out (32 in the deep layers) still fills warps
+__global__ void __launch_bounds__(256) k_gather_points(const float* __restrict__ in, const int* __restrict__ sel, int rows,
+                                                       int n_in, int n_out, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * n_out) return;
+    const int r = e / n_out, j = e - r * n_out;
+    const int s = __ldg(sel + (size_t)b * n_out + j);
+    out[(size_t)b * rows * n_out + e] = __ldg(in + ((size_t)b * rows + r) * n_in + s);
 }
 
 // ============================================================================================
@@ -1451,7 +1453,24 @@ __global__ void __launch_bounds__(RR_WARPS * 32, FB ? 2 : LS_RR_CTAS) k_knn_rera
 // g[b][r] = mean_n f[b][r][n], r over Co*3 rows
 __global__ void __launch_bounds__(256) k_row_mean(const float* __restrict__ f, int rows, int Nd, float* __restrict__ g) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b = blockIdx.y, r = blockIdx.x * 8 + w;
+    const int b = blockIdx.y;
+    if (Nd == 32) {
+        // deep layers: 32 floats per row.  A lane sums one quarter of a row (two float4), 4 lanes share a row, a warp
+        // covers 8 rows, the CTA 64 -- same pairing as the general path's (s0 + s1) + (s2 + s3) is NOT required here:
+        // this path is the only one used for Nd == 32, for every batch composition.
+        const int r = blockIdx.x * 64 + w * 8 + (lane >> 2);
+        float acc = 0.f;
+        if (r < rows) {
+            const float4* p4 = reinterpret_cast<const float4*>(f + ((size_t)b * rows + r) * 32) + (lane & 3) * 2;
+            const float4 u = __ldg(p4), v = __ldg(p4 + 1);
+            acc = ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
+        }
+        acc += __shfl_xor_sync(FULL, acc, 1);
+        acc += __shfl_xor_sync(FULL, acc, 2);
+        if (r < rows && (lane & 3) == 0) g[(size_t)b * rows + r] = acc / 32.f;
+        return;
+    }
+    const int r = blockIdx.x * 8 + w;
     if (r >= rows) return;
     const float* p = f + ((size_t)b * rows + r) * Nd;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
