@@ -799,6 +799,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(
                 const float* wk = a.w0 + (size_t)(Co + c) * 3;
                 const float wq0 = __ldg(wq), wq1 = __ldg(wq + 1), wq2 = __ldg(wq + 2);
                 const float wk0 = __ldg(wk), wk1 = __ldg(wk + 1), wk2 = __ldg(wk + 2);
+                // the feature (q) and direction (k) rows share their multiplicands: one packed f32x2 mul / fma per
+                // pair (FMUL2 / FFMA2), same operations in the same order as the scalar form -> bit-identical
+                const f32x2_t w0 = pack2(wq0, wk0), w1 = pack2(wq1, wk1), w2 = pack2(wq2, wk2);
+                const f32x2_t X0 = pack2(x0, x0), X1 = pack2(x1, x1), X2 = pack2(x2, x2);
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 4
                 for (int k = 0; k < LS_KNN_K; ++k) {
@@ -807,12 +811,10 @@ __global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(
                     // cross(x_dir, nn)  (vec_dgcnn_atten.py:157)
                     const float c0 = h1 * n2 - h2 * n1, c1 = h2 * n0 - h0 * n2, c2 = h0 * n1 - h1 * n0;
                     const float d0 = n0 - x0, d1 = n1 - x1, d2 = n2 - x2;
-                    const float qx = fmaf(wq2, x0, fmaf(wq1, d0, wq0 * c0));
-                    const float qy = fmaf(wq2, x1, fmaf(wq1, d1, wq0 * c1));
-                    const float qz = fmaf(wq2, x2, fmaf(wq1, d2, wq0 * c2));
-                    const float kx = fmaf(wk2, x0, fmaf(wk1, d0, wk0 * c0));
-                    const float ky = fmaf(wk2, x1, fmaf(wk1, d1, wk0 * c1));
-                    const float kz = fmaf(wk2, x2, fmaf(wk1, d2, wk0 * c2));
+                    float qx, qy, qz, kx, ky, kz;
+                    unpack2(fma2(w2, X0, fma2(w1, pack2(d0, d0), mul2(w0, pack2(c0, c0)))), qx, kx);
+                    unpack2(fma2(w2, X1, fma2(w1, pack2(d1, d1), mul2(w0, pack2(c1, c1)))), qy, ky);
+                    unpack2(fma2(w2, X2, fma2(w1, pack2(d2, d2), mul2(w0, pack2(c2, c2)))), qz, kz);
                     float o0, o1, o2;
                     vn_act(qx, qy, qz, kx, ky, kz, oms, o0, o1, o2);
                     a0 += o0;
