@@ -311,7 +311,7 @@ int launch_rerank(const RerankArgs& ra, int B, cudaStream_t st) {
         const int rc = launch_rerank_one<false>(ra, grid, st);
         if (rc != LS_OK) return rc;
     }
-    return launch_rerank_one<true>(ra, grid, st);
+    return launch_rerank_one<true>(ra, dim3((ra.Nd + RR_FB_Q - 1) / RR_FB_Q, B), st);
 }
 
 int launch_edge(int mode, const EdgeArgs& a, cudaStream_t st) {

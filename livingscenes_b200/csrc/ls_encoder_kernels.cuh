@@ -1292,6 +1292,7 @@ struct RerankArgs {
     float* dist_out;             // optional [B][Nd][16]
 };
 constexpr int RR_WARPS = 8, RR_QPW = 4;  // warps per CTA, consecutive queries per warp
+constexpr int RR_FB_Q = 1024;             // queries screened per CTA of the heavy-path launch
 constexpr int RR_DCH = 192, RR_NR = 4, RR_ROW = RR_DCH + 4;  // dims per chunk, rows per pass, padded row stride
 // Exact direct-form distances for the few lanes that `need` one: the warp loads the query chunk and up to RR_NR
 // needed candidate rows cooperatively (coalesced, all loads in flight together) into shared memory, then every
@@ -1368,8 +1369,8 @@ __device__ __forceinline__ unsigned ord_f32(float f) {  // order-preserving map 
 // FB = false: the common path (0 <= count <= 32, no distances wanted) ONLY; FB = true: the rare heavy paths only (overflowed
 // lists -> exact brute force, lists longer than 32 or all_exact -> exact distance for every candidate).  One kernel with
 // all three paths needs 128 registers (16 warps per SM) for a latency-bound warp-per-query loop; the common path alone
-// needs 64-80 and runs at 4 CTAs per SM (measured: re-rank 1.07 ms -> 0.94 at 3 CTAs -> 0.90 at 4).  The FB launch exits per
-// CTA when none of its 32 queries is flagged.
+// needs 64-80 and runs at 4 CTAs per SM (measured: re-rank 1.07 ms -> 0.94 at 3 CTAs -> 0.90 at 4).  The FB launch screens
+// 1024 queries per CTA and exits when none is flagged.
 #ifndef LS_RR_CTAS
 #define LS_RR_CTAS 4
 #endif
@@ -1382,14 +1383,41 @@ __global__ void __launch_bounds__(RR_WARPS * 32, FB ? 2 : LS_RR_CTAS) k_knn_rera
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.y, qbase = (blockIdx.x * RR_WARPS + w) * RR_QPW;
     const int n_pt_q = (a.Nd + KT_PTS - 1) / KT_PTS;
-    if (FB && !a.all_exact) {  // CTA-level early exit: is any of this CTA's RR_WARPS * RR_QPW queries flagged?
-        const int q = blockIdx.x * RR_WARPS * RR_QPW + (int)threadIdx.x;
-        int flagged = 0;
-        if (threadIdx.x < RR_WARPS * RR_QPW && q < a.Nd) {
-            const int c = __ldg(a.cand_cnt + ((size_t)b * n_pt_q + q / KT_PTS) * KT_PTS + q % KT_PTS);
-            flagged = c < 0 || c > 32;
+    if (FB) {
+        // heavy launch: ONE CTA screens RR_FB_Q consecutive queries of an instance (coalesced count loads), collects the
+        // flagged ones in shared memory and works them off warp by warp; without a flagged query it exits at once
+        // (the usual case: 256 CTAs of a few hundred cycles instead of one CTA per 32 queries)
+        __shared__ int s_list[RR_FB_Q];
+        __shared__ int s_n;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const int qblk = blockIdx.x * RR_FB_Q;
+        for (int i = threadIdx.x; i < RR_FB_Q; i += RR_WARPS * 32) {
+            const int q = qblk + i;
+            if (q < a.Nd) {
+                const int c = __ldg(a.cand_cnt + ((size_t)b * n_pt_q + q / KT_PTS) * KT_PTS + q % KT_PTS);
+                if (a.all_exact || c < 0 || c > 32) s_list[atomicAdd(&s_n, 1)] = q;
+            }
         }
-        if (!__syncthreads_or(flagged)) return;
+        __syncthreads();
+        const int n_flag = s_n;
+        const float* pms_f = a.pm_s + (size_t)b * a.Ns * Dp;
+        for (int i = w; i < n_flag; i += RR_WARPS) {
+            const int q = s_list[i];
+            const int c = __ldg(a.cand_cnt + ((size_t)b * n_pt_q + q / KT_PTS) * KT_PTS + q % KT_PTS);
+            const float* qrow = a.pm_q + ((size_t)b * a.Nd + q) * Dp;
+            const u64 lk = c < 0 ? knn_bruteforce_pm(qrow, sq_all[w], pms_f, a.Ns, Dp)
+                                 : knn_rerank(qrow, sq_all[w], pms_f,
+                                              a.cand + ((size_t)b * n_pt_q + q / KT_PTS) * KT_CAP * KT_PTS + q % KT_PTS, c, Dp);
+            if (lane < LS_KNN_K) {
+                const size_t o = ((size_t)b * a.Nd + q) * LS_KNN_K + lane;
+                const int64_t sv = max(0, min(key_idx(lk) & 0x7fffffff, a.Ns - 1));  // stay in bounds on NaN input
+                a.idx_out[o] = sv;
+                if (a.idx_tap) a.idx_tap[o] = sv;
+                if (a.dist_out) a.dist_out[o] = key_dist(lk);
+            }
+        }
+        return;
     }
     if (qbase >= a.Nd) return;
     const float* pms = a.pm_s + (size_t)b * a.Ns * Dp;
@@ -1417,21 +1445,8 @@ __global__ void __launch_bounds__(RR_WARPS * 32, FB ? 2 : LS_RR_CTAS) k_knn_rera
         const float* qrow = a.pm_q + ((size_t)b * a.Nd + q) * Dp;
         int s_out;
         float d_out = 0.f;
-        const bool heavy = c_j < 0 || c_j > 32 || a.all_exact;
-        if (heavy != FB) continue;  // the other launch's query
-        if (!FB) {
-            // (common path below)
-        } else if (c_j < 0) {
-            const u64 lk = knn_bruteforce_pm(qrow, sq, pms, a.Ns, Dp);
-            s_out = key_idx(lk) & 0x7fffffff;
-            d_out = key_dist(lk);
-        } else {
-            const int qt = q / KT_PTS;
-            const u64 lk = knn_rerank(qrow, sq, pms, a.cand + ((size_t)b * n_pt_q + qt) * KT_CAP * KT_PTS + q % KT_PTS, c_j, Dp);
-            s_out = key_idx(lk) & 0x7fffffff;
-            d_out = key_dist(lk);
-        }
-        if (!FB) {
+        if (c_j < 0 || c_j > 32 || a.all_exact) continue;  // the heavy launch's query
+        {
             const int cnt = c_j;
             u64 key = lane < cnt ? (((u64)ord_f32(cd_j) << 32) | (unsigned)ci_j) : KEY_MAX;
             key = warp_rank_sort(key, cnt, ssort[w]);
