@@ -653,10 +653,11 @@ int ls_encoder_forward(const ls_encoder_desc* d, const ls_encoder_io* io, void* 
             k_row_mean<<<dim3(Nd == 32 ? (Co * 3 + 63) / 64 : (Co * 3 + 7) / 8, B), 256, 0, st>>>(p.pooled, Co * 3, Nd, p.gmean);
             LS_CHECK_LAUNCH("k_row_mean");
             if (Co >= 128) {
-                // bias[b][r][a] = sum_c Wg2[r][c] g[b][c][a]: a warp per weight row, 8 instances per CTA
-                const size_t smem = (size_t)BIAS_BG * Co * 3 * sizeof(float);
+                // bias[b][r][a] = sum_c Wg2[r][c] g[b][c][a]: register-tiled, 128 rows x 8 instances per CTA
+                const size_t smem = ((size_t)BIAS_BG * (Co * 3 + 1) + (size_t)BIAS_ROWS * (BIAS_KT + 1)) * sizeof(float);
                 LS_CHECK_CUDA(cudaFuncSetAttribute(k_bias_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_bias_rows<<<dim3((2 * Co + 8 * BIAS_RPW - 1) / (8 * BIAS_RPW), (B + BIAS_BG - 1) / BIAS_BG), 256, smem, st>>>(p.gmean, Co, B, L.w_g2, p.bias);
+                k_bias_rows<<<dim3((2 * Co + BIAS_ROWS - 1) / BIAS_ROWS, (B + BIAS_BG - 1) / BIAS_BG), 256, smem, st>>>(p.gmean, Co, B, L.w_g2,
+                                                                                                                     p.bias);
                 LS_CHECK_LAUNCH("k_bias_rows");
             } else {
                 k_bias_gemv<<<dim3((2 * Co + 7) / 8, B), 256, (size_t)Co * 3 * sizeof(float), st>>>(p.gmean, Co, L.w_g2, p.bias);

@@ -1549,45 +1549,67 @@ __global__ void __launch_bounds__(256) k_bias_gemv(const float* __restrict__ g, 
     }
 }
 
-// The same bias for BG instances per CTA: a warp owns one weight row and reads it ONCE for the BG instances whose
-// pooled means sit in shared memory (the per-instance gemv re-read the 2 MB matrix of layer 6 for each of the 256
-// instances; the 48-CTA SIMT GEMM that replaced it in round 2 ran 0.11 ms for 0.8 GFLOP).  Accumulation order per
-// (instance, row): lanes stride the channels, then a shuffle tree -- independent of the batch composition.
-constexpr int BIAS_BG = 8, BIAS_RPW = 8;
+// bias[b][r][a] = sum_c Wg2[r][c] * g[b][c][a] for layers with Co >= 128, as a register-tiled FP32 GEMM: one CTA = 128
+// weight rows x 8 instances (24 columns), a thread owns 2 rows x 2 instances x 3 axes, the means of the 8 instances are
+// staged once in shared memory, the weight tile [128 rows][32 c] per step (next tile prefetched into registers).
+// (The per-instance gemv re-read the 2 MB matrix of layer 6 for each of the 256 instances; a 48-CTA SIMT GEMM took
+// 0.11 ms; a warp-per-row version with 24 shuffle reductions per row still 0.11 ms.)  Each output is one sequential
+// fp32 chain over c = 0..Co-1: independent of the batch composition.
+constexpr int BIAS_BG = 8, BIAS_ROWS = 128, BIAS_KT = 32;
 __global__ void __launch_bounds__(256) k_bias_rows(const float* __restrict__ g, int Co, int B, const float* __restrict__ wg2,
                                                    float* __restrict__ bias) {
-    extern __shared__ float sg[];  // [BIAS_BG][Co*3]
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b0 = blockIdx.y * BIAS_BG, nb = min(BIAS_BG, B - b0);
-    for (int i = threadIdx.x; i < BIAS_BG * Co * 3; i += blockDim.x)
-        sg[i] = (i / (Co * 3) < nb) ? g[(size_t)b0 * Co * 3 + i] : 0.f;
-    __syncthreads();
-#pragma unroll 1
-    for (int rr = 0; rr < BIAS_RPW; ++rr) {  // the staged means are reused for BIAS_RPW rows per warp
-        const int r = (blockIdx.x * 8 + w) * BIAS_RPW + rr;
-        if (r >= 2 * Co) return;
-        float acc[BIAS_BG][3];
+    extern __shared__ float sb[];
+    const int gs = Co * 3 + 1;                 // padded per-instance stride of the staged means
+    float* sg = sb;                            // [BIAS_BG][gs]
+    float* sw = sb + BIAS_BG * gs;             // [BIAS_ROWS][BIAS_KT + 1]
+    const int t = threadIdx.x;
+    const int b0 = blockIdx.y * BIAS_BG, nb = min(BIAS_BG, B - b0), r0 = blockIdx.x * BIAS_ROWS;
+    for (int i = t; i < BIAS_BG * Co * 3; i += 256) {
+        const int bi = i / (Co * 3), e = i - bi * (Co * 3);
+        sg[bi * gs + e] = bi < nb ? g[(size_t)(b0 + bi) * Co * 3 + e] : 0.f;
+    }
+    const int rg = t >> 2, cg = t & 3;         // rows r0 + 2 rg, + 1; instances 2 cg, 2 cg + 1
+    float acc[2][6];
 #pragma unroll
-        for (int bi = 0; bi < BIAS_BG; ++bi) acc[bi][0] = acc[bi][1] = acc[bi][2] = 0.f;
-        for (int c = lane; c < Co; c += 32) {
-            const float wv = __ldg(wg2 + (size_t)r * Co + c);
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int bi = 0; bi < BIAS_BG; ++bi) {
-                const float* gp = sg + bi * Co * 3 + c * 3;
-                acc[bi][0] = fmaf(wv, gp[0], acc[bi][0]);
-                acc[bi][1] = fmaf(wv, gp[1], acc[bi][1]);
-                acc[bi][2] = fmaf(wv, gp[2], acc[bi][2]);
+        for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+    float wr[BIAS_ROWS * BIAS_KT / 256];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < BIAS_ROWS * BIAS_KT / 256; ++i) {
+            const int row = i * 8 + (t >> 5), r = r0 + row;
+            wr[i] = (r < 2 * Co && k0 + (t & 31) < Co) ? __ldg(wg2 + (size_t)r * Co + k0 + (t & 31)) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < Co; k0 += BIAS_KT) {
+        __syncthreads();  // the previous tile is no longer read (and, first time, the means are staged)
+#pragma unroll
+        for (int i = 0; i < BIAS_ROWS * BIAS_KT / 256; ++i) sw[(i * 8 + (t >> 5)) * (BIAS_KT + 1) + (t & 31)] = wr[i];
+        if (k0 + BIAS_KT < Co) fetch(k0 + BIAS_KT);
+        __syncthreads();
+        const float* w0 = sw + (2 * rg) * (BIAS_KT + 1);
+        const float* g0 = sg + (2 * cg) * gs + k0 * 3;
+#pragma unroll 8
+        for (int k = 0; k < BIAS_KT; ++k) {
+            const float wa = w0[k], wb = w0[BIAS_KT + 1 + k];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const float gv = g0[(j / 3) * gs + k * 3 + (j % 3)];
+                acc[0][j] = fmaf(wa, gv, acc[0][j]);
+                acc[1][j] = fmaf(wb, gv, acc[1][j]);
             }
         }
+    }
 #pragma unroll
-        for (int bi = 0; bi < BIAS_BG; ++bi) {
-            const float s0 = warp_sum(acc[bi][0]), s1 = warp_sum(acc[bi][1]), s2 = warp_sum(acc[bi][2]);
-            if (lane == 0 && bi < nb) {
-                float* o = bias + ((size_t)(b0 + bi) * 2 * Co + r) * 3;
-                o[0] = s0;
-                o[1] = s1;
-                o[2] = s2;
-            }
+    for (int i = 0; i < 2; ++i) {
+        const int r = r0 + 2 * rg + i;
+        if (r >= 2 * Co) continue;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int bi = 2 * cg + j / 3;
+            if (bi < nb) bias[((size_t)(b0 + bi) * 2 * Co + r) * 3 + (j % 3)] = acc[i][j];
         }
     }
 }
