@@ -130,15 +130,20 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : KT_V32(KT_INOUT, v)::"memory");
 }
 // ------------------------------------------------------------------------------------------- pack
+constexpr int KP_LD = 36;  // padded row (floats) of the point-major transpose tile: 16-byte aligned, conflict-free float4 rows
 __global__ void __launch_bounds__(KT_PTS) k_knn_pack(const float* __restrict__ f, int D, int N, int n_pt, int n_kb,
                                                      float* __restrict__ img, float* __restrict__ nrm,
                                                      float* __restrict__ pm) {
-    const int b = blockIdx.y, pt = blockIdx.x, t = threadIdx.x;
+    // per warp: 32 points x 32 dims (4 k-blocks) staged for the point-major copy, so that 8 lanes write one point's 128
+    // contiguous bytes (a thread writing its own row piece touches 32 lines per instruction, half a sector each)
+    __shared__ __align__(16) float s_t[KT_PTS / 32][32 * KP_LD];
+    const int b = blockIdx.y, pt = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int p = pt * KT_PTS + t;
     const bool ok = p < N;
     const float* fb = f + (size_t)b * D * N;
     float* tile = img + ((size_t)b * n_pt + pt) * n_kb * KT_BLOCK;
     const int Dp = n_kb * KT_KB;
+    float* st = s_t[w];
     float nr = 0.f;
     for (int kb = 0; kb < n_kb; ++kb) {
         float x[KT_KB], h[KT_KB], l[KT_KB];
@@ -157,10 +162,28 @@ __global__ void __launch_bounds__(KT_PTS) k_knn_pack(const float* __restrict__ f
         *reinterpret_cast<float4*>(dst + 512 + t * 4) = make_float4(h[4], h[5], h[6], h[7]);
         *reinterpret_cast<float4*>(dst + KT_IMG + t * 4) = make_float4(l[0], l[1], l[2], l[3]);
         *reinterpret_cast<float4*>(dst + KT_IMG + 512 + t * 4) = make_float4(l[4], l[5], l[6], l[7]);
-        if (ok) {
-            float* row = pm + ((size_t)b * N + p) * Dp + kb * KT_KB;
-            *reinterpret_cast<float4*>(row) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(row + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        if ((n_kb & 3) != 0) {  // short feature vectors (layer 0: one k-block): direct row pieces
+            if (ok) {
+                float* row = pm + ((size_t)b * N + p) * Dp + kb * KT_KB;
+                *reinterpret_cast<float4*>(row) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(row + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+            continue;
+        }
+        float4* srow = reinterpret_cast<float4*>(st + lane * KP_LD + (kb & 3) * KT_KB);
+        srow[0] = make_float4(x[0], x[1], x[2], x[3]);
+        srow[1] = make_float4(x[4], x[5], x[6], x[7]);
+        if ((kb & 3) == 3) {
+            __syncwarp();
+            const int p0 = pt * KT_PTS + w * 32;  // first point of this warp
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = 4 * i + (lane >> 3);
+                const float4 v = *reinterpret_cast<const float4*>(st + q * KP_LD + 4 * (lane & 7));
+                if (p0 + q < N)
+                    *reinterpret_cast<float4*>(pm + ((size_t)b * N + p0 + q) * Dp + (kb - 3) * KT_KB + 4 * (lane & 7)) = v;
+            }
+            __syncwarp();
         }
     }
     nrm[((size_t)b * n_pt + pt) * KT_PTS + t] = ok ? nr : __int_as_float(0x7f800000);
