@@ -792,6 +792,16 @@ __global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(
             const float x0 = __ldg(xyz + n), x1 = __ldg(xyz + Ns + n), x2 = __ldg(xyz + 2 * Ns + n);
             const float nr = fmaxf(sqrtf(fmaf(x2, x2, fmaf(x1, x1, x0 * x0))), EPS_NRM);
             const float h0 = x0 / nr, h1 = x1 / nr, h2 = x2 / nr;
+            // the edge geometry (cross product and difference) does not depend on the channel: lane k < 16 computes it
+            // for edge k once, the channel loop below picks it up with shuffles (same operations: bit-identical)
+            float e_c0, e_c1, e_c2, e_d0, e_d1, e_d2;
+            {
+                const int m = sIdx[ql][lane & (LS_KNN_K - 1)];
+                const float n0 = __ldg(xyz + m), n1 = __ldg(xyz + Ns + m), n2 = __ldg(xyz + 2 * Ns + m);
+                // cross(x_dir, nn)  (vec_dgcnn_atten.py:157)
+                e_c0 = h1 * n2 - h2 * n1, e_c1 = h2 * n0 - h0 * n2, e_c2 = h0 * n1 - h1 * n0;
+                e_d0 = n0 - x0, e_d1 = n1 - x1, e_d2 = n2 - x2;
+            }
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 const int c = j * 32 + lane;
@@ -806,11 +816,8 @@ __global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 4
                 for (int k = 0; k < LS_KNN_K; ++k) {
-                    const int m = sIdx[ql][k];
-                    const float n0 = __ldg(xyz + m), n1 = __ldg(xyz + Ns + m), n2 = __ldg(xyz + 2 * Ns + m);
-                    // cross(x_dir, nn)  (vec_dgcnn_atten.py:157)
-                    const float c0 = h1 * n2 - h2 * n1, c1 = h2 * n0 - h0 * n2, c2 = h0 * n1 - h1 * n0;
-                    const float d0 = n0 - x0, d1 = n1 - x1, d2 = n2 - x2;
+                    const float c0 = __shfl_sync(FULL, e_c0, k), c1 = __shfl_sync(FULL, e_c1, k), c2 = __shfl_sync(FULL, e_c2, k);
+                    const float d0 = __shfl_sync(FULL, e_d0, k), d1 = __shfl_sync(FULL, e_d1, k), d2 = __shfl_sync(FULL, e_d2, k);
                     float qx, qy, qz, kx, ky, kz;
                     unpack2(fma2(w2, X0, fma2(w1, pack2(d0, d0), mul2(w0, pack2(c0, c0)))), qx, kx);
                     unpack2(fma2(w2, X1, fma2(w1, pack2(d1, d1), mul2(w0, pack2(c1, c1)))), qy, ky);

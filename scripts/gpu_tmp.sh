@@ -1,5 +1,10 @@
-O=gpurun_out/r2final
-mkdir -p $O
-timeout 300 python scripts/sanitize_small.py 2>&1 | tail -2
-timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_small.py > $O/memcheck.log 2>&1; tail -6 $O/memcheck.log
-timeout 2400 compute-sanitizer --tool racecheck --print-limit 20 python scripts/sanitize_small.py > $O/racecheck.log 2>&1; tail -6 $O/racecheck.log
+mkdir -p gpurun_out/r2
+timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_configs.py -x -q -k "teacher or free_running or batch_consistency or encode or wave_schedule or c2 or c3" 2>&1 | tail -3
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-c4 --no-sdf > gpurun_out/r2/ab31.json 2> gpurun_out/r2/ab31.err
+tail -2 gpurun_out/r2/ab31.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r2/ab31.json"))
+st=d["stages_ms"]
+print("L0 shuffles + head row split", round(d["value"]), round(d["ms_per_step"],3), d["checked"], st["knn_edgeconv[0]"], st["head"])
+PY
