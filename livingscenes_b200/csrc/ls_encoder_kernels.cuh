@@ -848,14 +848,11 @@ __global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(
     constexpr int CH = CG / LPP;
     const int sub = lane / LPP, gl = lane % LPP;
     auto ld4 = [](const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); };
-    auto add4 = [](float4 x, float4 y) { return make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w); };
+    // (packed f32x2 adds / products: same IEEE operations in the same order as the scalar forms, half the instructions --
+    //  the deep layers are bound by instruction issue, not by their gathers: profiles/r02/experiments.md section 12)
+    auto add4 = [](float4 x, float4 y) { return add4_packed(x, y); };
     // VN leaky-ReLU on 4 channels at once: q[axis], k[axis] hold the 4 channels of one axis
-    auto act4 = [&](const float4* q, const float4* k, float4* o) {
-        vn_act(q[0].x, q[1].x, q[2].x, k[0].x, k[1].x, k[2].x, oms, o[0].x, o[1].x, o[2].x);
-        vn_act(q[0].y, q[1].y, q[2].y, k[0].y, k[1].y, k[2].y, oms, o[0].y, o[1].y, o[2].y);
-        vn_act(q[0].z, q[1].z, q[2].z, k[0].z, k[1].z, k[2].z, oms, o[0].z, o[1].z, o[2].z);
-        vn_act(q[0].w, q[1].w, q[2].w, k[0].w, k[1].w, k[2].w, oms, o[0].w, o[1].w, o[2].w);
-    };
+    auto act4 = [&](const float4* q, const float4* k, float4* o) { vn_act4(q, k, oms, o); };
     auto store_out = [&](int c4, int n, const float4* v, float sc) {
         float* o = a.out + ((size_t)b * Co + c4) * ostride + n;
 #pragma unroll
