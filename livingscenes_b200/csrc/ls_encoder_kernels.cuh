@@ -589,8 +589,11 @@ __device__ __noinline__ SelRet knn_select_slow(u64 k0, u64 k1, u64 k2, u64 k3, u
 #ifndef LS_P2_CTAS
 #define LS_P2_CTAS 3
 #endif
+#ifndef LS_P2_WIDE_CPL
+#define LS_P2_WIDE_CPL 8  // c_out >= 256: 2 CTAs per SM (128 registers): these layers are issue bound and spill at 80
+#endif
 template <int MODE, int CPL, bool P1 = true>
-__global__ void __launch_bounds__(EDGE_THREADS, P1 ? 2 : LS_P2_CTAS) k_knn_edge(const EdgeArgs a) {
+__global__ void __launch_bounds__(EDGE_THREADS, (P1 || CPL >= LS_P2_WIDE_CPL) ? 2 : LS_P2_CTAS) k_knn_edge(const EdgeArgs a) {
     // phase-1 tiles and phase-2 scratch share one buffer
     constexpr int TILE_FLOATS = P1 ? 2 * DKC * (QT + ST) : 4;
     constexpr int SR_FLOATS = (MODE == MODE_ATT) ? 8 * (CPL > 4 ? CPL / 4 : 1) * LS_KNN_K * 8 : 0;
