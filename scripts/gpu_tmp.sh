@@ -1,10 +1,4 @@
-mkdir -p gpurun_out/r2
-timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q -k "knn or free_running or batch_consistency" 2>&1 | tail -3
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-c4 --no-sdf > gpurun_out/r2/ab35.json 2> gpurun_out/r2/ab35.err
-tail -2 gpurun_out/r2/ab35.err
-python - <<PY
-import json
-d=json.load(open("gpurun_out/r2/ab35.json"))
-st=d["stages_ms"]
-print("filter ffma2", round(d["value"]), round(d["ms_per_step"],3), d["checked"], {k:v for k,v in st.items() if "filter" in k})
-PY
+O=gpurun_out/r2final
+mkdir -p $O
+timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python scripts/sanitize_small.py > $O/memcheck.log 2>&1; grep -c "Invalid\|out of bounds\|misaligned" $O/memcheck.log; tail -3 $O/memcheck.log
+timeout 2400 compute-sanitizer --tool racecheck --print-limit 20 python scripts/sanitize_small.py > $O/racecheck.log 2>&1; tail -2 $O/racecheck.log
