@@ -132,6 +132,44 @@ def test_decoder_packing_is_consistent():
     assert torch.allclose(full4, split4, atol=1e-5)
 
 
+def test_tc_packed_floats_accounts_for_both_tile_formats():
+    """ls_tc_packed_floats (host-only entry point): the packed buffer holds the 128-row-tile images of k_gemm_tc /
+    k_gemm_tc2 and, for R > 128, the 256-row-tile images of k_gemm_tc3 behind them (hi + lo, k-blocks of 16)."""
+    import ctypes as C
+
+    from livingscenes_b200 import _lib
+
+    def packed(R, K):
+        n = C.c_size_t(0)
+        assert _lib.lib().ls_tc_packed_floats(R, K, C.byref(n)) == 0
+        return n.value
+
+    ceil = lambda a, b: -(-a // b)
+    for R, K in ((64, 32), (128, 64), (129, 64), (256, 32), (257, 512), (768, 768), (2048, 256), (1, 1)):
+        kb = ceil(K, 16)
+        want = ceil(R, 128) * kb * 2 * 128 * 16 + (ceil(R, 256) * kb * 2 * 256 * 16 if R > 128 else 0)
+        assert packed(R, K) == want, (R, K)
+    n = C.c_size_t(0)
+    assert _lib.lib().ls_tc_packed_floats(0, 8, C.byref(n)) != 0  # invalid sizes are rejected, not clamped
+
+
+def test_roofline_traffic_file_is_reproducible_from_the_committed_launch_list(tmp_path):
+    """profiles/knn_edgeconv_traffic.json (bench.py's roofline.traffic) is exactly what scripts/summarize_launches.py
+    derives from the committed ncu launch list of the final commit."""
+    import json
+
+    out = tmp_path / "traffic.json"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "summarize_launches.py"),
+                        os.path.join(ROOT, "profiles", "r02", "launches_fwd.csv"), "--traffic", str(out)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got, want = json.load(open(out)), json.load(open(os.path.join(ROOT, "profiles", "knn_edgeconv_traffic.json")))
+    for layer in range(7):
+        k = f"layer{layer}_dram_bytes_per_launch"
+        assert got[k] == want[k] and got[k] > 0, k
+    assert "k_knn_edge" in r.stdout and "k_gemm_tc3" in r.stdout
+
+
 def test_shard_ranges_cover_and_are_contiguous():
     from livingscenes_b200.dist import shard_range
 
